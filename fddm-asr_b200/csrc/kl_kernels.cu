@@ -1,0 +1,503 @@
+// kl_kernels.cu -- fused diffusion-KL forward (+backward) over token rows.
+//
+// Replaces SchedulerAdapter.kl_term (reference train.py:190-255): softmax over the vocab, the two
+// closed-form transition products, the un-normalised posteriors q and p_theta (+eps, quirk Q5), the
+// per-token KL, the masked per-sample mean and the batch mean -- and, for training, d loss/d logits --
+// in ONE pass over the logits (algorithmic traffic: s bytes/element forward, 2s forward+backward).
+//
+// Closed forms used per row (a_t = 1-beta_t, b_t = beta_t/K, a_p/b_p the same at t-1, beta_0 := 0;
+// e_k = exp(z_k - max z), S = sum e, xh_k = e_k/S, eps = 1e-8):
+//   P = b_t + a_t*xh[xt] + eps                      Q = b_t + a_t*[x0==xt] + eps
+//   generic k (k != xt, k != x0):  q_g = b_t*b_p/Q,  p_k + eps = c1*e_k + c0,
+//                                  c1 = b_t*a_p/(S*P), c0 = b_t*b_p/P + eps
+//   KL_row   = q_g * sum_k (log(q_g+eps) - log(p_k+eps))  (+ exact corrections for k in {xt, x0})
+//   backward : r_k = q_k/(p_k+eps),  S' = sum_k r_k p_k,  g_k = -r_k u_k a_p/P + [k=xt] a_t S'/P,
+//              dKL/dz_n = xh_n (g_n - sum_m g_m xh_m)
+// so the per-element work is one exp, one log (and one reciprocal for the gradient); the <=2 special
+// entries are patched with their exact values.
+#include <math.h>
+
+#include "rowkit.cuh"
+
+namespace fddm {
+namespace {
+
+struct KlWorkspace {
+  unsigned int next_row;     // dynamic row scheduler (self-resetting)
+  unsigned int done_ctas;    // completion counter (self-resetting)
+  unsigned int pad[30];
+  float kl_tok[1];           // [rows]
+};
+
+struct KlParams {
+  const void* logits;
+  const int64_t* xt;
+  const int64_t* x0;
+  const int64_t* t;
+  const uint8_t* mask;
+  const float* betas;
+  const float* grad_scale;
+  KlWorkspace* ws;
+  float* loss_out;
+  void* grad;
+  int T, B, L, V, rows;
+  float inv_bdiv;            // 1 / batch divisor
+};
+
+constexpr float kEps = 1e-8f;
+constexpr float kLn2 = 0.69314718055994530942f;
+
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// weight of one token in the loss: mask/(sum_l mask + eps)/Bdiv, or 1/L/Bdiv without a mask
+// (train.py:249-255).  Evaluated by one full warp.
+__device__ __forceinline__ float token_weight_warp(const KlParams& p, int row, int lane) {
+  const int b = row / p.L;
+  if (p.mask == nullptr) return (1.0f / static_cast<float>(p.L)) * p.inv_bdiv;
+  const uint8_t* mrow = p.mask + static_cast<size_t>(b) * p.L;
+  int c = 0;
+  for (int l = lane; l < p.L; l += 32) c += (mrow[l] != 0);
+  c = warp_sum_int(c);
+  const bool on = p.mask[row] != 0;
+  return on ? (1.0f / (static_cast<float>(c) + kEps)) * p.inv_bdiv : 0.0f;
+}
+
+__device__ __forceinline__ void load_betas(const KlParams& p, int b, float& beta_t, float& beta_p) {
+  long long tt = p.t[b];
+  tt = tt < 1 ? 1 : (tt > p.T ? p.T : tt);
+  beta_t = p.betas[tt - 1];
+  beta_p = (tt == 1) ? 0.0f : p.betas[tt - 2];          // beta_0 := 0  (train.py:214-217)
+}
+
+// ------------------------------------------------------------------------------------------------
+// the row math, shared by the register-resident and the shared-memory-resident paths
+// ------------------------------------------------------------------------------------------------
+template <int NT, bool BWD, typename T, class Row>
+__device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt, const int x0, const float z_xt,
+                                             const float z_x0, const float beta_t, const float beta_p,
+                                             const float wscale, float* red, T* grad_row) {
+  const float Kf = static_cast<float>(V);
+  const float a_t = 1.0f - beta_t, b_t = beta_t / Kf;
+  const float a_p = 1.0f - beta_p, b_p = beta_p / Kf;
+
+  // pass 1: row max
+  float m = kNegInf;
+  row.for_each([&](int, float& x) { m = fmaxf(m, x); });
+  m = block_max<NT>(m, red);
+
+  // pass 2: e_k = exp(z_k - m) kept in place, S = sum e_k
+  float s1[1] = {0.0f};
+  row.for_each([&](int, float& x) {
+    x = __expf(x - m);
+    s1[0] += x;
+  });
+  block_sum<NT, 1>(s1, red);
+  const float inv_S = 1.0f / s1[0];
+
+  const bool same = (xt == x0);
+  const float e_xt = __expf(z_xt - m), e_x0 = __expf(z_x0 - m);
+  const float xh_xt = e_xt * inv_S, xh_x0 = e_x0 * inv_S;
+  const float P = (b_t + a_t * xh_xt) + kEps;
+  const float Q = (b_t + (same ? a_t : 0.0f)) + kEps;
+  const float inv_P = 1.0f / P;
+  const float q_g = b_t * b_p / Q;
+  const float lq2 = __log2f(q_g + kEps);
+  const float c1 = b_t * a_p * inv_S * inv_P;
+  const float c0 = b_t * b_p * inv_P + kEps;
+  const float cg = q_g * b_t * a_p * inv_P;
+
+  // pass 3: generic terms for every k
+  float a3[BWD ? 3 : 1];
+#pragma unroll
+  for (int i = 0; i < (BWD ? 3 : 1); ++i) a3[i] = 0.0f;
+  row.for_each([&](int, float& e) {
+    const float y = fmaf(c1, e, c0);
+    a3[0] += lq2 - __log2f(y);
+    if (BWD) {
+      const float rc = __fdividef(1.0f, y);
+      a3[1] += rc;
+      a3[2] = fmaf(rc, e, a3[2]);
+    }
+  });
+  block_sum<NT, (BWD ? 3 : 1)>(a3, red);
+
+  // exact corrections for the special entries (computed redundantly by every thread)
+  float kl = q_g * (kLn2 * a3[0]);
+  float Sp = BWD ? q_g * (Kf - kEps * a3[1]) : 0.0f;
+  float G = BWD ? -cg * inv_S * a3[2] : 0.0f;
+  float r_sp[2], u_sp[2], xh_sp[2];
+  const int n_sp = same ? 1 : 2;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (i < n_sp) {
+      const bool is_xt = (i == 0);
+      const float e = is_xt ? e_xt : e_x0;
+      const float xh = is_xt ? xh_xt : xh_x0;
+      const float u = is_xt ? (b_t + a_t) : b_t;                       // train.py:227
+      const float v = (same || !is_xt) ? (a_p + b_p) : b_p;            // train.py:230
+      // what the generic formulas contributed for this k
+      const float y = fmaf(c1, e, c0);
+      const float rc = __fdividef(1.0f, y);
+      kl -= q_g * (kLn2 * (lq2 - __log2f(y)));
+      // its true value
+      const float qk = u * v / Q;
+      const float pk = u * (a_p * xh + b_p) * inv_P;
+      const float rk = qk / (pk + kEps);
+      kl += qk * (logf(qk + kEps) - logf(pk + kEps));
+      if (BWD) {
+        Sp += rk * pk - q_g * (1.0f - kEps * rc);
+        G += cg * rc * xh;                                             // remove generic g_k*xh_k
+        r_sp[i] = rk; u_sp[i] = u; xh_sp[i] = xh;
+      }
+    }
+  }
+  if (BWD) {
+    float g_sp[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (i < n_sp) {
+        g_sp[i] = -r_sp[i] * u_sp[i] * a_p * inv_P + (i == 0 ? a_t * Sp * inv_P : 0.0f);
+        G += g_sp[i] * xh_sp[i];
+      }
+    }
+    // pass 4: gradient, generic entries from registers ...
+    const float A = -wscale * inv_S * cg;
+    const float Bc = -wscale * inv_S * G;
+    row.store(grad_row, [&](int, float e) {
+      const float y = fmaf(c1, e, c0);
+      const float rc = __fdividef(1.0f, y);
+      return e * fmaf(A, rc, Bc);
+    });
+    // ... then the special entries overwritten with their exact values
+    consumer_sync<NT>();
+    if (threadIdx.x == 0) {
+      Vec16<T>::store1(grad_row + xt, wscale * xh_sp[0] * (g_sp[0] - G));
+      if (!same) Vec16<T>::store1(grad_row + x0, wscale * xh_sp[1] * (g_sp[1] - G));
+    }
+  }
+  return kl;
+}
+
+// last CTA: masked per-sample means and the batch mean, in a fixed order (deterministic)
+template <int NT>
+__device__ __forceinline__ void kl_finalize(const KlParams& p, float* red, int tid) {
+  constexpr int NW = NT / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  float acc = 0.0f;
+  for (int b = warp; b < p.B; b += NW) {
+    float s = 0.0f;
+    int c = 0;
+    for (int l = lane; l < p.L; l += 32) {
+      const size_t i = static_cast<size_t>(b) * p.L + l;
+      const float k = __ldcg(&p.ws->kl_tok[i]);
+      if (p.mask) {
+        const bool on = p.mask[i] != 0;
+        c += on;
+        s += on ? k : 0.0f;
+      } else {
+        s += k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    c = warp_sum_int(c);
+    acc += p.mask ? s / (static_cast<float>(c) + kEps) : s / static_cast<float>(p.L);
+  }
+  if (lane == 0) red[warp] = acc;
+  consumer_sync<NT>();
+  if (tid == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < NW; ++w) tot += red[w];
+    *p.loss_out = tot * p.inv_bdiv;
+    p.ws->next_row = 0;
+    p.ws->done_ctas = 0;
+    __threadfence();
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void kl_epilogue(const KlParams& p, float* red, int* s_flag, int tid) {
+  consumer_sync<NT>();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int d = atomicAdd(&p.ws->done_ctas, 1u);
+    *s_flag = (d == gridDim.x - 1);
+  }
+  consumer_sync<NT>();
+  if (*s_flag) {
+    __threadfence();
+    kl_finalize<NT>(p, red, tid);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: TMA ring + register-resident rows
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NT, int EPT, bool BWD>
+__global__ void __launch_bounds__(NT + 32, (NT <= 256 ? 2 : 1))
+kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_bytes) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages];
+  __shared__ RingMeta s_meta[kMaxStages];
+  __shared__ float s_red[4 * 32];
+  __shared__ int s_flag;
+
+  Ring ring;
+  ring.stages = dyn_smem;
+  ring.stage_bytes = stage_bytes;
+  ring.nstages = nstages;
+  ring.full = s_full;
+  ring.empty = s_empty;
+  ring.meta = s_meta;
+  ring_init<NT>(ring);
+
+  const int tid = threadIdx.x;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.V) * sizeof(T);
+
+  if (tid >= NT) {
+    // ===== producer warp =====
+    const int lane = tid - NT;
+    int s = 0;
+    uint32_t round = 0;
+    for (;;) {
+      if (round > 0) mbar_wait(&ring.empty[s], (round - 1) & 1);
+      int row = 0;
+      if (lane == 0) row = static_cast<int>(atomicAdd(&p.ws->next_row, 1u));
+      row = __shfl_sync(0xffffffffu, row, 0);
+      if (row >= p.rows) {
+        if (lane == 0) {
+          ring.meta[s].row = -1;
+          mbar_arrive(&ring.full[s]);
+        }
+        break;
+      }
+      const float w = token_weight_warp(p, row, lane);
+      if (lane == 0) {
+        RingMeta mt;
+        mt.row = row;
+        mt.w = w;
+        mt.i0 = static_cast<int>(p.xt[row]);
+        mt.i1 = static_cast<int>(p.x0[row]);
+        load_betas(p, row / p.L, mt.f0, mt.f1);
+        mt.f2 = 0.0f; mt.f3 = 0.0f;
+        ring.meta[s] = mt;
+        if (w != 0.0f) {
+          mbar_arrive_expect_tx(&ring.full[s], row_bytes);
+          tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
+                      row_bytes, &ring.full[s]);
+        } else {
+          mbar_arrive(&ring.full[s]);
+        }
+      }
+      if (++s == nstages) { s = 0; ++round; }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
+  RegRow<T, NT, EPT> row;
+  row.tid = tid;
+  row.nvec = p.V / RegRow<T, NT, EPT>::N;
+  int s = 0;
+  uint32_t round = 0;
+  for (;;) {
+    mbar_wait(&ring.full[s], round & 1);
+    const RingMeta mt = ring.meta[s];
+    if (mt.row < 0) break;
+    T* grad_row = BWD ? static_cast<T*>(p.grad) + static_cast<size_t>(mt.row) * p.V : nullptr;
+    if (mt.w == 0.0f) {
+      ring_release(ring, s);
+      if (BWD) row.store(grad_row, [](int, float) { return 0.0f; });
+      if (tid == 0) p.ws->kl_tok[mt.row] = 0.0f;
+    } else {
+      const T* st = reinterpret_cast<const T*>(ring.stage(s));
+      row.load_from_smem(st, p.V, tid);
+      const float z_xt = Vec16<T>::load1(st + mt.i0);
+      const float z_x0 = Vec16<T>::load1(st + mt.i1);
+      ring_release(ring, s);
+      const float kl = kl_row_math<NT, BWD, T>(row, p.V, mt.i0, mt.i1, z_xt, z_x0, mt.f0, mt.f1, mt.w * gscale, s_red,
+                                               grad_row);
+      if (tid == 0) p.ws->kl_tok[mt.row] = kl;
+    }
+    if (++s == nstages) { s = 0; ++round; }
+  }
+  kl_epilogue<NT>(p, s_red, &s_flag, tid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic path: any V <= FDDM_MAX_VOCAB, any alignment; the row is an fp32 copy in shared memory
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NT, bool BWD>
+__global__ void __launch_bounds__(NT, 1) kl_rows_generic_kernel(const KlParams p) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ float s_red[4 * 32];
+  __shared__ int s_flag;
+  float* srow = reinterpret_cast<float*>(dyn_smem);
+  const int tid = threadIdx.x;
+  const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
+  SmemRow<T, NT> row;
+  for (int r = blockIdx.x; r < p.rows; r += gridDim.x) {
+    const float w = token_weight_warp(p, r, tid & 31);
+    T* grad_row = BWD ? static_cast<T*>(p.grad) + static_cast<size_t>(r) * p.V : nullptr;
+    if (w == 0.0f) {
+      if (BWD) for (int k = tid; k < p.V; k += NT) Vec16<T>::store1(grad_row + k, 0.0f);
+      if (tid == 0) p.ws->kl_tok[r] = 0.0f;
+      continue;
+    }
+    const T* src = static_cast<const T*>(p.logits) + static_cast<size_t>(r) * p.V;
+    row.load_from_gmem(srow, src, p.V, tid);
+    const int xt = static_cast<int>(p.xt[r]), x0 = static_cast<int>(p.x0[r]);
+    const float z_xt = srow[xt], z_x0 = srow[x0];
+    float beta_t, beta_p;
+    load_betas(p, r / p.L, beta_t, beta_p);
+    consumer_sync<NT>();      // everyone has read the specials before pass 2 overwrites the row
+    const float kl = kl_row_math<NT, BWD, T>(row, p.V, xt, x0, z_xt, z_x0, beta_t, beta_p, w * gscale, s_red, grad_row);
+    if (tid == 0) p.ws->kl_tok[r] = kl;
+    consumer_sync<NT>();      // row buffer is reused by the next iteration
+  }
+  kl_epilogue<NT>(p, s_red, &s_flag, tid);
+}
+
+// x *= num/den, all CTAs leave immediately when the ratio is exactly 1
+template <typename T>
+__global__ void __launch_bounds__(256) scale_inplace_kernel(T* x, int64_t nvec, int64_t n, const float* num,
+                                                            const float* den) {
+  const float r = __ldg(num) / (den ? __ldg(den) : 1.0f);
+  if (r == 1.0f) return;
+  constexpr int N = Vec16<T>::N;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 v = *(reinterpret_cast<const uint4*>(x) + i);
+    float f[N];
+    Vec16<T>::unpack(v, f);
+#pragma unroll
+    for (int e = 0; e < N; ++e) f[e] *= r;
+    *(reinterpret_cast<uint4*>(x) + i) = Vec16<T>::pack(f);
+  }
+  // tail (n not a multiple of the vector width)
+  if (blockIdx.x == 0) {
+    for (int64_t k = nvec * N + threadIdx.x; k < n; k += blockDim.x) Vec16<T>::store1(x + k, Vec16<T>::load1(x + k) * r);
+  }
+}
+
+template <typename T, bool BWD>
+int launch_kl(const KlParams& p, cudaStream_t stream) {
+  const size_t row_bytes = static_cast<size_t>(p.V) * sizeof(T);
+  const bool aligned = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
+                       (!BWD || reinterpret_cast<uintptr_t>(p.grad) % 16 == 0);
+  const int sms = num_sms();
+  if (aligned && p.V <= 32768) {
+    int nt, ept;
+    if (p.V <= 4096) { nt = 128; ept = 32; }
+    else if (p.V <= 8192) { nt = 256; ept = 32; }
+    else if (p.V <= 16384) { nt = 512; ept = 32; }
+    else { nt = 512; ept = 64; }
+    const RingPlan plan = plan_ring(row_bytes, nt);
+    if (plan.nstages >= 1) {
+      const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
+      const uint32_t sb = static_cast<uint32_t>((row_bytes + 127) & ~size_t(127));
+#define FDDM_KL_LAUNCH(NT_, EPT_)                                                                           \
+  do {                                                                                                      \
+    auto kfn = kl_rows_ring_kernel<T, NT_, EPT_, BWD>;                                                      \
+    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                      static_cast<int>(plan.smem_bytes)));                                  \
+    kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb);                                  \
+  } while (0)
+      if (nt == 128) FDDM_KL_LAUNCH(128, 32);
+      else if (nt == 256) FDDM_KL_LAUNCH(256, 32);
+      else if (ept == 32) FDDM_KL_LAUNCH(512, 32);
+      else FDDM_KL_LAUNCH(512, 64);
+#undef FDDM_KL_LAUNCH
+      FDDM_LAUNCH_OK();
+      return FDDM_OK;
+    }
+  }
+  // generic path
+  const size_t smem = static_cast<size_t>(p.V) * sizeof(float) + 128;
+  auto kfn = kl_rows_generic_kernel<T, 256, BWD>;
+  FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * 4));
+  kfn<<<grid, 256, smem, stream>>>(p);
+  FDDM_LAUNCH_OK();
+  return FDDM_OK;
+}
+
+int kl_entry(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
+             const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V, double batch_div,
+             const float* grad_scale, void* workspace, float* loss_out, void* grad_logits, bool bwd,
+             cudaStream_t stream) {
+  FDDM_CHECK_ARG(logits && xt && x0 && t && betas && workspace && loss_out, "kl: null pointer argument");
+  FDDM_CHECK_ARG(!bwd || grad_logits, "kl: grad_logits is null");
+  FDDM_CHECK_ARG(dtype_valid(dtype), "kl: bad dtype %d", dtype);
+  FDDM_CHECK_ARG(B > 0 && L > 0 && V > 1 && T > 0, "kl: non-positive size B=%lld L=%lld V=%lld T=%lld", (long long)B,
+                 (long long)L, (long long)V, (long long)T);
+  FDDM_CHECK_ARG(B * L < (1ll << 31), "kl: too many rows");
+  FDDM_CHECK_ARG(batch_div > 0.0, "kl: batch_div must be positive");
+  if (V > FDDM_MAX_VOCAB) {
+    set_error("kl: V=%lld exceeds FDDM_MAX_VOCAB=%d", (long long)V, FDDM_MAX_VOCAB);
+    return FDDM_EUNSUPPORTED;
+  }
+  KlParams p;
+  p.logits = logits; p.xt = xt; p.x0 = x0; p.t = t; p.mask = x_mask; p.betas = betas;
+  p.grad_scale = grad_scale; p.ws = static_cast<KlWorkspace*>(workspace); p.loss_out = loss_out;
+  p.grad = grad_logits;
+  p.T = static_cast<int>(T); p.B = static_cast<int>(B); p.L = static_cast<int>(L); p.V = static_cast<int>(V);
+  p.rows = static_cast<int>(B * L);
+  p.inv_bdiv = static_cast<float>(1.0 / batch_div);
+  if (dtype == FDDM_F32) return bwd ? launch_kl<float, true>(p, stream) : launch_kl<float, false>(p, stream);
+  if (dtype == FDDM_BF16)
+    return bwd ? launch_kl<__nv_bfloat16, true>(p, stream) : launch_kl<__nv_bfloat16, false>(p, stream);
+  return bwd ? launch_kl<__half, true>(p, stream) : launch_kl<__half, false>(p, stream);
+}
+
+}  // namespace
+}  // namespace fddm
+
+extern "C" {
+
+size_t fddm_kl_workspace_bytes(int64_t B, int64_t L) {
+  if (B <= 0 || L <= 0) return 0;
+  return 128 + static_cast<size_t>(B) * static_cast<size_t>(L) * sizeof(float);
+}
+
+int fddm_kl_forward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
+                    const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
+                    double batch_div, void* workspace, float* loss_out, fddm_stream_t stream) {
+  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, betas, T, B, L, V, batch_div, nullptr, workspace, loss_out,
+                        nullptr, false, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fddm_kl_forward_backward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
+                             const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
+                             double batch_div, const float* grad_scale, void* workspace, float* loss_out,
+                             void* grad_logits, fddm_stream_t stream) {
+  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, betas, T, B, L, V, batch_div, grad_scale, workspace,
+                        loss_out, grad_logits, true, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fddm_scale_inplace(void* x, int dtype, int64_t n, const float* num, const float* den, fddm_stream_t stream_) {
+  using namespace fddm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FDDM_CHECK_ARG(x && num, "scale_inplace: null pointer");
+  FDDM_CHECK_ARG(dtype_valid(dtype), "scale_inplace: bad dtype %d", dtype);
+  FDDM_CHECK_ARG(n >= 0, "scale_inplace: negative size");
+  FDDM_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0, "scale_inplace: x must be 16-byte aligned");
+  if (n == 0) return FDDM_OK;
+  const int grid = num_sms() * 8;
+  if (dtype == FDDM_F32) {
+    scale_inplace_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(x), n / 4, n, num, den);
+  } else if (dtype == FDDM_BF16) {
+    scale_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(x), n / 8, n, num, den);
+  } else {
+    scale_inplace_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<__half*>(x), n / 8, n, num, den);
+  }
+  FDDM_LAUNCH_OK();
+  return FDDM_OK;
+}
+
+}  // extern "C"

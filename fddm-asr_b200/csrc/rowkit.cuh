@@ -1,0 +1,160 @@
+// rowkit.cuh -- row stores and the TMA producer/consumer ring used by every token-row kernel.
+//
+// CTA shape of a "ring" kernel: NT consumer threads (threadIdx.x < NT) + one producer warp
+// (threadIdx.x >= NT).  The producer warp claims token rows from a global work counter (dynamic
+// scheduling: masked rows cost nothing, so static striding would leave SMs idle), prepares the
+// row's metadata, and issues one cp.async.bulk per input stream into the next free ring stage.
+// Consumers wait on the stage's `full` mbarrier, pull the row into registers, hand the stage back
+// through the `empty` mbarrier (one arrive per consumer warp) and do all the math from registers
+// while the producer is already fetching rows for later iterations.
+#pragma once
+
+#include "common.cuh"
+
+namespace fddm {
+
+constexpr int kMaxStages = 4;
+constexpr float kNegInf = -3.0e38f;   // finite stand-in for -inf in padded lanes (no inf-inf NaNs)
+
+// ------------------------------------------------------------------------------------------------
+// RegRow: the row lives in EPT fp32 registers per thread.  Thread `tid` owns the 16-byte vectors
+// tid, tid+NT, tid+2NT, ... of the row; lanes past the end of the row are inactive.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NT, int EPT>
+struct RegRow {
+  static constexpr int N = Vec16<T>::N;       // elements per 16-byte vector
+  static constexpr int NVEC = EPT / N;
+  static_assert(EPT % N == 0, "EPT must be a whole number of vectors");
+  float v[EPT];
+  int nvec;                                   // vectors in the row (V / N)
+  int tid;
+
+  __device__ __forceinline__ void load_from_smem(const void* stage, int V, int tid_) {
+    tid = tid_;
+    nvec = V / N;
+    const uint4* s = reinterpret_cast<const uint4*>(stage);
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int vi = j * NT + tid;
+      if (vi < nvec) {
+        Vec16<T>::unpack(s[vi], &v[j * N]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[j * N + e] = kNegInf;
+      }
+    }
+  }
+  // f(k, x&) over the valid elements owned by this thread, ascending k within the thread
+  template <class F>
+  __device__ __forceinline__ void for_each(F&& f) {
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int vi = j * NT + tid;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) f(vi * N + e, v[j * N + e]);
+      }
+    }
+  }
+  // dst[k] = g(k, x) for the whole row, 128-bit streaming stores
+  template <class G>
+  __device__ __forceinline__ void store(T* dst, G&& g) {
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int vi = j * NT + tid;
+      if (vi < nvec) {
+        float o[N];
+#pragma unroll
+        for (int e = 0; e < N; ++e) o[e] = g(vi * N + e, v[j * N + e]);
+        stg_stream_v4(reinterpret_cast<uint4*>(dst) + vi, Vec16<T>::pack(o));
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// SmemRow: generic path, the row is an fp32 array in shared memory (any V, any alignment).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NT>
+struct SmemRow {
+  float* r;
+  int V;
+  int tid;
+  __device__ __forceinline__ void load_from_gmem(float* smem_row, const T* src, int V_, int tid_) {
+    r = smem_row; V = V_; tid = tid_;
+    for (int k = tid; k < V; k += NT) r[k] = Vec16<T>::load1(src + k);
+    consumer_sync<NT>();
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each(F&& f) {
+    for (int k = tid; k < V; k += NT) f(k, r[k]);
+  }
+  template <class G>
+  __device__ __forceinline__ void store(T* dst, G&& g) {
+    for (int k = tid; k < V; k += NT) Vec16<T>::store1(dst + k, g(k, r[k]));
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Ring bookkeeping shared by producer and consumers
+// ------------------------------------------------------------------------------------------------
+struct RingMeta {          // one per stage, written by the producer before it arms `full`
+  int row;                 // token row index, -1 = no more work
+  float w;                 // row weight (0 => nothing was loaded for this row)
+  int i0, i1;              // per-kernel integers (token ids)
+  float f0, f1, f2, f3;    // per-kernel scalars (schedule coefficients)
+};
+
+struct Ring {
+  uint8_t* stages;         // nstages * stage_bytes, 128-byte aligned
+  uint32_t stage_bytes;
+  int nstages;
+  uint64_t* full;          // [kMaxStages]
+  uint64_t* empty;         // [kMaxStages]
+  RingMeta* meta;          // [kMaxStages]
+
+  __device__ __forceinline__ uint8_t* stage(int s) const { return stages + static_cast<size_t>(s) * stage_bytes; }
+};
+
+// Called by all threads of the CTA (consumers + producer warp) before the role split.
+template <int NT>
+__device__ __forceinline__ void ring_init(Ring& ring) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ring.nstages; ++s) {
+      mbar_init(&ring.full[s], 1);
+      mbar_init(&ring.empty[s], NT / 32);
+    }
+    mbar_fence_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+}
+
+// Consumer side: hand a stage back to the producer once this warp has finished reading it.
+__device__ __forceinline__ void ring_release(Ring& ring, int s) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&ring.empty[s]);
+}
+
+// host: choose the ring depth for a given per-stage footprint
+struct RingPlan {
+  int nstages;
+  int ctas_per_sm;
+  size_t smem_bytes;       // dynamic shared memory per CTA
+};
+static inline RingPlan plan_ring(size_t stage_bytes, int nt_consumers) {
+  RingPlan p{};
+  const size_t sb = (stage_bytes + 127) & ~size_t(127);
+  const size_t budget_total = 216 * 1024;   // leave room for static smem + driver reservation
+  int ctas = (nt_consumers <= 256) ? 2 : 1;
+  size_t per = budget_total / ctas;
+  int st = static_cast<int>(per / sb);
+  if (st < 2 && ctas == 2) { ctas = 1; per = budget_total; st = static_cast<int>(per / sb); }
+  if (st > kMaxStages) st = kMaxStages;
+  p.nstages = st;          // may be 0 -> caller falls back / reports unsupported
+  p.ctas_per_sm = ctas;
+  p.smem_bytes = sb * static_cast<size_t>(st > 0 ? st : 0) + 128;
+  return p;
+}
+
+}  // namespace fddm

@@ -1,0 +1,585 @@
+// sample_kernels.cu -- the two resampling kernels of the token path.
+//
+//  * sample_q_ids  : SchedulerAdapter.sample_q (reference train.py:180-188) fused ids -> ids.  The
+//    one-hot [B,L,V] tensor, q_sample's five passes over it and torch.multinomial's exponential_/
+//    div/argmax are replaced by one streaming pass over the injected Exp(1) noise (4 B/element) or
+//    by in-kernel Philox (no memory traffic at all).  For a one-hot x0 the row of q_sample takes two
+//    values (p_hi at x0, p_lo elsewhere, sched:44-49), so the kernel evaluates
+//    argmax_k fdiv(p_k, E_k) with the reference's fp32 roundings and lowest-index tie rule.
+//  * jump_step     : DiffusionJumpySampler._jump_once minus the decoder (sampler:189-215): softmax,
+//    Delta-step posterior for a one-hot x_t (sched:186-206) or alpha-bar mix (sampler:139-151), then
+//    argmax / exponential-race sampling (== Categorical.sample(), sampler:153-162).
+//
+// Elementwise steps that decide ids use __fmul_rn/__fadd_rn/__fdiv_rn so that nvcc cannot contract
+// them into FMAs: the op order is the reference's.
+#include <math.h>
+
+#include <algorithm>
+
+#include "rowkit.cuh"
+
+namespace fddm {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// noise sources
+// ------------------------------------------------------------------------------------------------
+struct NoiseMem {           // injected Exp(1) variates for one row (shared or global memory)
+  const float* p;
+  bool vec_ok;              // row pointer 16-byte aligned
+  __device__ __forceinline__ void load4(int k0, float* E) const {
+    if (vec_ok) {
+      const float4 v = *reinterpret_cast<const float4*>(p + k0);
+      E[0] = v.x; E[1] = v.y; E[2] = v.z; E[3] = v.w;
+    } else {
+      E[0] = p[k0]; E[1] = p[k0 + 1]; E[2] = p[k0 + 2]; E[3] = p[k0 + 3];
+    }
+  }
+  __device__ __forceinline__ float load1(int k) const { return p[k]; }
+};
+
+struct NoisePhilox {        // counter = (k/4 within the row, row, offset); lane k%4 of the output
+  uint2 key;
+  uint32_t row;
+  uint2 off;
+  __device__ __forceinline__ void load4(int k0, float* E) const {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(k0 >> 2), row, off.x, off.y), key);
+    E[0] = exp1_from_bits(r.x); E[1] = exp1_from_bits(r.y);
+    E[2] = exp1_from_bits(r.z); E[3] = exp1_from_bits(r.w);
+  }
+  __device__ __forceinline__ float load1(int k) const {
+    float E[4];
+    load4(k & ~3, E);
+    return E[k & 3];
+  }
+};
+
+// f(k, x&, E_k) over a RegRow / SmemRow
+template <typename T, int NT, int EPT, class Noise, class F>
+__device__ __forceinline__ void for_each_noise(RegRow<T, NT, EPT>& row, const Noise& nz, F&& f) {
+  constexpr int N = RegRow<T, NT, EPT>::N;
+#pragma unroll
+  for (int j = 0; j < RegRow<T, NT, EPT>::NVEC; ++j) {
+    const int vi = j * NT + row.tid;
+    if (vi < row.nvec) {
+      float E[N];
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) nz.load4(vi * N + 4 * q, E + 4 * q);
+#pragma unroll
+      for (int e = 0; e < N; ++e) f(vi * N + e, row.v[j * N + e], E[e]);
+    }
+  }
+}
+template <typename T, int NT, class Noise, class F>
+__device__ __forceinline__ void for_each_noise(SmemRow<T, NT>& row, const Noise& nz, F&& f) {
+  for (int k = row.tid; k < row.V; k += NT) f(k, row.r[k], nz.load1(k));
+}
+
+#ifndef FDDM_JUMP_DT
+// ------------------------------------------------------------------------------------------------
+// sample_q_ids
+// ------------------------------------------------------------------------------------------------
+struct SampleQParams {
+  const int64_t* x0;
+  const int64_t* t;
+  const float* alpha_bar;
+  const float* noise;
+  int64_t* out;
+  int T, L, K, rows;
+  float eps, u;              // u = fp32(1/K)  (sched:45)
+  uint2 key, off;
+};
+
+// the two values of the q_sample row for one-hot x0, with the reference's roundings (sched:44-49)
+__device__ __forceinline__ void q_sample_two_values(float ab, float u, float eps, int K, float& p_hi, float& p_lo) {
+  const float lo_raw = __fmul_rn(__fsub_rn(1.0f, ab), u);          // ab*0 + (1-ab)*u
+  const float hi_raw = __fadd_rn(ab, lo_raw);                       // ab*1 + (1-ab)*u
+  const float hi_c = fmaxf(hi_raw, eps), lo_c = fmaxf(lo_raw, eps); // clamp_min(eps), quirk Q4
+  // row sum: one p_hi and K-1 p_lo; evaluated in fp64 then rounded (torch's fp32 tree differs by <=1ulp)
+  const float s = fmaxf(static_cast<float>(static_cast<double>(hi_c) + static_cast<double>(K - 1) * lo_c), eps);
+  p_hi = __fdiv_rn(hi_c, s);
+  p_lo = __fdiv_rn(lo_c, s);
+}
+
+template <int NT, bool PHILOX>
+__global__ void __launch_bounds__(NT) sample_q_kernel(const SampleQParams p) {
+  __shared__ float s_red[4 * 32];
+  const int tid = threadIdx.x;
+  const bool vec = (p.K % 4 == 0) && (PHILOX || reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
+  for (int row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const int b = row / p.L;
+    long long tt = p.t[b];
+    tt = tt < 1 ? 1 : (tt > p.T ? p.T : tt);
+    const float ab = p.alpha_bar[tt - 1];
+    float p_hi, p_lo;
+    q_sample_two_values(ab, p.u, p.eps, p.K, p_hi, p_lo);
+    const int x0 = static_cast<int>(p.x0[row]);
+    float best = -1.0f;
+    int best_k = 0x7fffffff;
+    auto visit = [&](int k, float E) {
+      const float sc = __fdiv_rn(k == x0 ? p_hi : p_lo, E);
+      if (sc > best) { best = sc; best_k = k; }                    // strict: earlier index keeps ties
+    };
+    NoisePhilox ph;
+    ph.key = p.key; ph.row = static_cast<uint32_t>(row); ph.off = p.off;
+    const float* nrow = PHILOX ? nullptr : p.noise + static_cast<size_t>(row) * p.K;
+    if (vec) {
+      const int nvec = p.K / 4;
+      constexpr int U = 4;
+      int vi = tid;
+      for (; vi + (U - 1) * NT < nvec; vi += U * NT) {
+        float E[U][4];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          if (PHILOX) {
+            ph.load4((vi + j * NT) * 4, E[j]);
+          } else {
+            const uint4 v = ldg_stream_v4(nrow + (vi + j * NT) * 4);
+            E[j][0] = __uint_as_float(v.x); E[j][1] = __uint_as_float(v.y);
+            E[j][2] = __uint_as_float(v.z); E[j][3] = __uint_as_float(v.w);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) visit((vi + j * NT) * 4 + e, E[j][e]);
+        }
+      }
+      for (; vi < nvec; vi += NT) {
+        float E[4];
+        if (PHILOX) {
+          ph.load4(vi * 4, E);
+        } else {
+          const uint4 v = ldg_stream_v4(nrow + vi * 4);
+          E[0] = __uint_as_float(v.x); E[1] = __uint_as_float(v.y);
+          E[2] = __uint_as_float(v.z); E[3] = __uint_as_float(v.w);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) visit(vi * 4 + e, E[e]);
+      }
+    } else {
+      for (int k = tid; k < p.K; k += NT) visit(k, PHILOX ? ph.load1(k) : nrow[k]);
+    }
+    block_argmax<NT>(best, best_k, s_red);
+    if (tid == 0) p.out[row] = best_k;
+  }
+}
+
+#endif  // !FDDM_JUMP_DT
+
+// ------------------------------------------------------------------------------------------------
+// jump_step
+// ------------------------------------------------------------------------------------------------
+}  // namespace
+
+// Shared by the per-dtype translation units (this file is compiled once per logits dtype with
+// -DFDDM_JUMP_DT=<n> for the kernels, and once without it for the C entry points).
+struct JumpParams {
+  const void* logits;
+  const int64_t* x_t;
+  const float* coeffs;       // exact: a_cum[B] | b_cum[B] | a_tgt[B] | b_tgt[B] | identity
+  const float* alpha_bar;    // fast
+  const float* noise;
+  int64_t* x_out;
+  int64_t* argmax_p_out;     // optional: argmax_k p_x0 (the sampler's final x_0, sampler:292)
+  void* p_out;
+  unsigned int* work;        // dynamic row counter (self-resetting pair: next, done)
+  int B, L, K, rows;
+  int flags;
+  int abar_index;
+  float temperature, eps, u;
+  uint2 key, off;
+};
+int jump_launch_f32(const JumpParams& p, int noise, cudaStream_t stream);
+int jump_launch_bf16(const JumpParams& p, int noise, cudaStream_t stream);
+int jump_launch_f16(const JumpParams& p, int noise, cudaStream_t stream);
+
+#ifdef FDDM_JUMP_DT
+namespace {
+
+struct JumpRowCtx {
+  int xt;
+  float a_c, b_c, a_g, b_g;  // exact
+  float ab;                  // fast
+  bool identity;
+};
+
+// One row: returns the new id (valid in every thread).  `NoiseT` provides E_k when sampling.
+template <int NT, typename T, class Row, class NoiseT>
+__device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, const JumpRowCtx& c, const NoiseT& nz,
+                                             float* red, T* p_row_out, int* argmax_p) {
+  const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
+  const bool sample = (p.flags & FDDM_JUMP_SAMPLE) != 0;
+  const bool write_p = (p.flags & FDDM_JUMP_WRITE_P) != 0;
+
+  // softmax in the logits dtype (F.softmax, sampler:189): exp(z-m)/S, rounded to T
+  float m = kNegInf;
+  row.for_each([&](int, float& x) { m = fmaxf(m, x); });
+  m = block_max<NT>(m, red);
+  float s1[1] = {0.0f};
+  row.for_each([&](int, float& x) {
+    x = expf(x - m);
+    s1[0] += x;
+  });
+  block_sum<NT, 1>(s1, red);
+  const float S = s1[0];
+  float s2[1] = {0.0f};
+  float pm = -1.0f;
+  int pm_k = 0x7fffffff;
+  row.for_each([&](int k, float& x) {
+    x = Vec16<T>::round_trip(__fdiv_rn(x, S));
+    s2[0] += x;
+    if (x > pm) { pm = x; pm_k = k; }
+  });
+  if (write_p) row.store(p_row_out, [](int, float x) { return x; });
+  if (argmax_p != nullptr) {
+    block_argmax<NT>(pm, pm_k, red);
+    *argmax_p = pm_k;
+  }
+  if (c.identity) return c.xt;                                     // sched:133-134 (delta <= 0)
+
+  // un-normalised target distribution val_k, evaluated on the fly
+  float bs = 0.0f, A_gen = 0.0f, A_xt = 0.0f, ab = 0.0f, mixu = 0.0f;
+  float sum_xh = 0.0f;
+  if (exact) {
+    block_sum<NT, 1>(s2, red);
+    sum_xh = s2[0];
+    bs = __fmul_rn(c.b_g, sum_xh);                                 // b_tgt * sum(x0hat)     sched:191
+    A_gen = c.b_c;                                                 // a*0 + b*sum_xt*1       sched:187
+    A_xt = __fadd_rn(c.a_c, c.b_c);
+  } else {
+    ab = c.ab;
+    const float uT = Vec16<T>::round_trip(p.u);                    // full((1,1,K), 1/K, dtype)  sampler:147
+    mixu = Vec16<T>::round_trip(__fmul_rn(__fsub_rn(1.0f, ab), uT));   // (1-abar)*u         sampler:151
+  }
+  auto value = [&](int k, float xh) -> float {
+    if (exact) {
+      const float Bk = __fadd_rn(__fmul_rn(c.a_g, xh), bs);
+      return __fmul_rn(k == c.xt ? A_xt : A_gen, Bk);
+    }
+    return Vec16<T>::round_trip(__fadd_rn(Vec16<T>::round_trip(__fmul_rn(ab, xh)), mixu));
+  };
+
+  float best = -1.0f;
+  int best_k = 0x7fffffff;
+  if (!sample) {
+    row.for_each([&](int k, float& xh) {
+      const float v = value(k, xh);
+      if (v > best) { best = v; best_k = k; }
+    });
+  } else if (p.temperature == 1.0f) {
+    for_each_noise(row, nz, [&](int k, float& xh, float E) {
+      const float sc = __fdiv_rn(value(k, xh), E);
+      if (sc > best) { best = sc; best_k = k; }
+    });
+  } else {
+    // temperature path (sampler:159-161): probs = softmax(log(clamp(p_norm, 1e-12)) / tau).
+    // exact mode needs the normalised posterior (sched:200-204); fast mode uses the mix as is.
+    float scale = 1.0f, dn = 1.0f;
+    if (exact) {
+      // denom = a*x0hat[xt] + b*sum_xh*sum_xt ; x0hat[xt] is held by exactly one thread
+      float d1[1] = {0.0f};
+      row.for_each([&](int k, float& xh) { if (k == c.xt) d1[0] = xh; });
+      block_sum<NT, 1>(d1, red);
+      dn = fmaxf(__fadd_rn(__fmul_rn(c.a_c, d1[0]), __fmul_rn(c.b_c, sum_xh)), p.eps);
+      float ps[1] = {0.0f};
+      row.for_each([&](int k, float& xh) { ps[0] += __fdiv_rn(value(k, xh), dn); });
+      block_sum<NT, 1>(ps, red);
+      scale = fmaxf(ps[0], p.eps);
+    }
+    const float inv_tau = 1.0f / p.temperature;
+    auto logit_of = [&](int k, float xh) -> float {
+      float pn = value(k, xh);
+      if (exact) pn = __fdiv_rn(__fdiv_rn(pn, dn), scale);
+      return logf(fmaxf(pn, 1e-12f)) * inv_tau;
+    };
+    float m2 = kNegInf;
+    row.for_each([&](int k, float& xh) { m2 = fmaxf(m2, logit_of(k, xh)); });
+    m2 = block_max<NT>(m2, red);
+    for_each_noise(row, nz, [&](int k, float& xh, float E) {
+      const float sc = __fdiv_rn(expf(logit_of(k, xh) - m2), E);
+      if (sc > best) { best = sc; best_k = k; }
+    });
+  }
+  block_argmax<NT>(best, best_k, red);
+  return best_k;
+}
+
+__device__ __forceinline__ void jump_load_ctx(const JumpParams& p, int row, JumpRowCtx& c) {
+  const int b = row / p.L;
+  c.xt = static_cast<int>(p.x_t[row]);
+  c.identity = false;
+  c.a_c = c.b_c = c.a_g = c.b_g = 0.0f;
+  c.ab = 1.0f;
+  if (p.flags & FDDM_JUMP_EXACT) {
+    c.a_c = p.coeffs[b];
+    c.b_c = p.coeffs[p.B + b];
+    c.a_g = p.coeffs[2 * p.B + b];
+    c.b_g = p.coeffs[3 * p.B + b];
+    c.identity = p.coeffs[4 * p.B] != 0.0f;
+  } else {
+    c.ab = (p.abar_index < 0) ? 1.0f : p.alpha_bar[p.abar_index];
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void jump_epilogue(const JumpParams& p, int tid) {
+  consumer_sync<NT>();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int d = atomicAdd(&p.work[1], 1u);
+    if (d == gridDim.x - 1) {
+      p.work[0] = 0;
+      p.work[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// fast path: TMA ring (logits row [+ noise row] per stage) + register-resident rows
+template <typename T, int NT, int EPT, int NOISE /*0 none, 1 memory, 2 philox*/>
+__global__ void __launch_bounds__(NT + 32, (NT <= 256 ? 2 : 1))
+jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stage_bytes, const uint32_t noise_off) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages];
+  __shared__ RingMeta s_meta[kMaxStages];
+  __shared__ float s_red[4 * 32];
+
+  Ring ring;
+  ring.stages = dyn_smem;
+  ring.stage_bytes = stage_bytes;
+  ring.nstages = nstages;
+  ring.full = s_full;
+  ring.empty = s_empty;
+  ring.meta = s_meta;
+  ring_init<NT>(ring);
+
+  const int tid = threadIdx.x;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.K) * sizeof(T);
+  const uint32_t noise_bytes = static_cast<uint32_t>(p.K) * sizeof(float);
+
+  if (tid >= NT) {
+    if (tid == NT) {       // one producer lane is enough: no per-row reduction here
+      int s = 0;
+      uint32_t round = 0;
+      for (;;) {
+        if (round > 0) mbar_wait(&ring.empty[s], (round - 1) & 1);
+        const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
+        if (row >= p.rows) {
+          ring.meta[s].row = -1;
+          mbar_arrive(&ring.full[s]);
+          break;
+        }
+        JumpRowCtx c;
+        jump_load_ctx(p, row, c);
+        RingMeta mt;
+        mt.row = row; mt.w = c.identity ? 0.0f : 1.0f; mt.i0 = c.xt; mt.i1 = 0;
+        mt.f0 = (p.flags & FDDM_JUMP_EXACT) ? c.a_c : c.ab;
+        mt.f1 = c.b_c; mt.f2 = c.a_g; mt.f3 = c.b_g;
+        ring.meta[s] = mt;
+        mbar_arrive_expect_tx(&ring.full[s], row_bytes + (NOISE == 1 ? noise_bytes : 0u));
+        tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
+                    row_bytes, &ring.full[s]);
+        if (NOISE == 1)
+          tma_load_1d(ring.stage(s) + noise_off, p.noise + static_cast<size_t>(row) * p.K, noise_bytes, &ring.full[s]);
+        if (++s == nstages) { s = 0; ++round; }
+      }
+    }
+    return;
+  }
+
+  RegRow<T, NT, EPT> row;
+  int s = 0;
+  uint32_t round = 0;
+  for (;;) {
+    mbar_wait(&ring.full[s], round & 1);
+    const RingMeta mt = ring.meta[s];
+    if (mt.row < 0) break;
+    JumpRowCtx c;
+    c.xt = mt.i0; c.identity = (mt.w == 0.0f);
+    c.a_c = mt.f0; c.ab = mt.f0; c.b_c = mt.f1; c.a_g = mt.f2; c.b_g = mt.f3;
+    row.load_from_smem(ring.stage(s), p.K, tid);
+    if (NOISE != 1) ring_release(ring, s);
+    T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K : nullptr;
+    int amax = 0;
+    int id;
+    if (NOISE == 2) {
+      NoisePhilox nz;
+      nz.key = p.key; nz.row = static_cast<uint32_t>(mt.row); nz.off = p.off;
+      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+    } else {
+      NoiseMem nz;
+      nz.p = reinterpret_cast<const float*>(ring.stage(s) + noise_off);
+      nz.vec_ok = true;
+      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+    }
+    if (NOISE == 1) ring_release(ring, s);
+    if (tid == 0) {
+      p.x_out[mt.row] = id;
+      if (p.argmax_p_out) p.argmax_p_out[mt.row] = amax;
+    }
+    if (++s == nstages) { s = 0; ++round; }
+  }
+  jump_epilogue<NT>(p, tid);
+}
+
+// generic path
+template <typename T, int NT, int NOISE>
+__global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpParams p) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ float s_red[4 * 32];
+  float* srow = reinterpret_cast<float*>(dyn_smem);
+  const int tid = threadIdx.x;
+  SmemRow<T, NT> row;
+  for (int r = blockIdx.x; r < p.rows; r += gridDim.x) {
+    JumpRowCtx c;
+    jump_load_ctx(p, r, c);
+    row.load_from_gmem(srow, static_cast<const T*>(p.logits) + static_cast<size_t>(r) * p.K, p.K, tid);
+    T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(r) * p.K : nullptr;
+    int amax = 0;
+    int id;
+    if (NOISE == 2) {
+      NoisePhilox nz;
+      nz.key = p.key; nz.row = static_cast<uint32_t>(r); nz.off = p.off;
+      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+    } else {
+      NoiseMem nz;
+      nz.p = (NOISE == 1) ? p.noise + static_cast<size_t>(r) * p.K : nullptr;
+      nz.vec_ok = false;
+      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+    }
+    if (tid == 0) {
+      p.x_out[r] = id;
+      if (p.argmax_p_out) p.argmax_p_out[r] = amax;
+    }
+    consumer_sync<NT>();
+  }
+}
+
+template <typename T, int NOISE>
+int launch_jump(const JumpParams& p, cudaStream_t stream) {
+  const size_t row_bytes = static_cast<size_t>(p.K) * sizeof(T);
+  const size_t noise_bytes = (NOISE == 1) ? static_cast<size_t>(p.K) * sizeof(float) : 0;
+  bool aligned = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
+                 (!(p.flags & FDDM_JUMP_WRITE_P) || reinterpret_cast<uintptr_t>(p.p_out) % 16 == 0);
+  if (NOISE == 1) aligned = aligned && (noise_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
+  const int sms = num_sms();
+  if (aligned && p.K <= 32768 && p.work != nullptr) {
+    int nt, ept;
+    if (p.K <= 4096) { nt = 128; ept = 32; }
+    else if (p.K <= 8192) { nt = 256; ept = 32; }
+    else if (p.K <= 16384) { nt = 512; ept = 32; }
+    else { nt = 512; ept = 64; }
+    const size_t row_pad = (row_bytes + 127) & ~size_t(127);
+    const RingPlan plan = plan_ring(row_pad + noise_bytes, nt);
+    if (plan.nstages >= 1) {
+      const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
+      const uint32_t sb = static_cast<uint32_t>((row_pad + noise_bytes + 127) & ~size_t(127));
+#define FDDM_JUMP_LAUNCH(NT_, EPT_)                                                                         \
+  do {                                                                                                      \
+    auto kfn = jump_rows_ring_kernel<T, NT_, EPT_, NOISE>;                                                  \
+    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                      static_cast<int>(plan.smem_bytes)));                                  \
+    kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb, static_cast<uint32_t>(row_pad));  \
+  } while (0)
+      if (nt == 128) FDDM_JUMP_LAUNCH(128, 32);
+      else if (nt == 256) FDDM_JUMP_LAUNCH(256, 32);
+      else if (ept == 32) FDDM_JUMP_LAUNCH(512, 32);
+      else FDDM_JUMP_LAUNCH(512, 64);
+#undef FDDM_JUMP_LAUNCH
+      FDDM_LAUNCH_OK();
+      return FDDM_OK;
+    }
+  }
+  const size_t smem = static_cast<size_t>(p.K) * sizeof(float) + 128;
+  auto kfn = jump_rows_generic_kernel<T, 256, NOISE>;
+  FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * 4));
+  kfn<<<grid, 256, smem, stream>>>(p);
+  FDDM_LAUNCH_OK();
+  return FDDM_OK;
+}
+
+}  // namespace
+
+#if FDDM_JUMP_DT == 0
+#define FDDM_JUMP_T float
+#define FDDM_JUMP_FN jump_launch_f32
+#elif FDDM_JUMP_DT == 1
+#define FDDM_JUMP_T __nv_bfloat16
+#define FDDM_JUMP_FN jump_launch_bf16
+#else
+#define FDDM_JUMP_T __half
+#define FDDM_JUMP_FN jump_launch_f16
+#endif
+int FDDM_JUMP_FN(const JumpParams& p, int noise, cudaStream_t stream) {
+  if (noise == 0) return launch_jump<FDDM_JUMP_T, 0>(p, stream);
+  if (noise == 1) return launch_jump<FDDM_JUMP_T, 1>(p, stream);
+  return launch_jump<FDDM_JUMP_T, 2>(p, stream);
+}
+#endif  // FDDM_JUMP_DT
+}  // namespace fddm
+
+#ifndef FDDM_JUMP_DT
+extern "C" {
+
+int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_bar, int64_t T, int64_t B, int64_t L,
+                      int64_t K, float eps, const float* exp_noise, uint64_t seed, uint64_t offset, int64_t* xt_out,
+                      fddm_stream_t stream_) {
+  using namespace fddm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FDDM_CHECK_ARG(x0 && t && alpha_bar && xt_out, "sample_q_ids: null pointer argument");
+  FDDM_CHECK_ARG(B > 0 && L > 0 && K > 1 && T > 0, "sample_q_ids: non-positive size");
+  FDDM_CHECK_ARG(B * L < (1ll << 31) && K < (1ll << 30), "sample_q_ids: size too large");
+  SampleQParams p;
+  p.x0 = x0; p.t = t; p.alpha_bar = alpha_bar; p.noise = exp_noise; p.out = xt_out;
+  p.T = static_cast<int>(T); p.L = static_cast<int>(L); p.K = static_cast<int>(K);
+  p.rows = static_cast<int>(B * L);
+  p.eps = eps;
+  p.u = static_cast<float>(1.0 / static_cast<double>(K));
+  p.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  p.off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
+  const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(num_sms()) * 8));
+  if (exp_noise) sample_q_kernel<256, false><<<grid, 256, 0, stream>>>(p);
+  else sample_q_kernel<256, true><<<grid, 256, 0, stream>>>(p);
+  FDDM_LAUNCH_OK();
+  return FDDM_OK;
+}
+
+int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const float* coeffs, const float* alpha_bar,
+                   int64_t abar_index, int64_t B, int64_t L, int64_t K, int flags, float temperature, float eps,
+                   const float* exp_noise, uint64_t seed, uint64_t offset, void* workspace, int64_t* x_out,
+                   int64_t* argmax_p_out, void* p_x0_out, fddm_stream_t stream_) {
+  using namespace fddm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FDDM_CHECK_ARG(logits && x_t && x_out, "jump_step: null pointer argument");
+  FDDM_CHECK_ARG(dtype_valid(dtype), "jump_step: bad dtype %d", dtype);
+  FDDM_CHECK_ARG(B > 0 && L > 0 && K > 1, "jump_step: non-positive size");
+  FDDM_CHECK_ARG(B * L < (1ll << 31), "jump_step: too many rows");
+  FDDM_CHECK_ARG(!(flags & FDDM_JUMP_EXACT) || coeffs, "jump_step: exact mode needs coeffs");
+  FDDM_CHECK_ARG((flags & FDDM_JUMP_EXACT) || alpha_bar || abar_index < 0, "jump_step: fast mode needs alpha_bar");
+  FDDM_CHECK_ARG(!(flags & FDDM_JUMP_WRITE_P) || p_x0_out, "jump_step: WRITE_P needs p_x0_out");
+  FDDM_CHECK_ARG(temperature > 0.0f, "jump_step: temperature must be positive");
+  if (K > FDDM_MAX_VOCAB) {
+    set_error("jump_step: K=%lld exceeds FDDM_MAX_VOCAB=%d", (long long)K, FDDM_MAX_VOCAB);
+    return FDDM_EUNSUPPORTED;
+  }
+  JumpParams p;
+  p.logits = logits; p.x_t = x_t; p.coeffs = coeffs; p.alpha_bar = alpha_bar; p.noise = exp_noise;
+  p.x_out = x_out; p.argmax_p_out = argmax_p_out; p.p_out = p_x0_out;
+  p.work = static_cast<unsigned int*>(workspace);
+  p.B = static_cast<int>(B); p.L = static_cast<int>(L); p.K = static_cast<int>(K); p.rows = static_cast<int>(B * L);
+  p.flags = flags; p.abar_index = static_cast<int>(abar_index);
+  p.temperature = temperature; p.eps = eps;
+  p.u = static_cast<float>(1.0 / static_cast<double>(K));
+  p.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  p.off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
+  const bool sample = (flags & FDDM_JUMP_SAMPLE) != 0;
+  const int noise = !sample ? 0 : (exp_noise ? 1 : 2);
+  if (dtype == FDDM_F32) return jump_launch_f32(p, noise, stream);
+  if (dtype == FDDM_BF16) return jump_launch_bf16(p, noise, stream);
+  return jump_launch_f16(p, noise, stream);
+}
+
+}  // extern "C"
+#endif  // !FDDM_JUMP_DT

@@ -1,0 +1,17 @@
+"""fddm_b200 -- B200-native (sm_100a) categorical discrete-diffusion token path of FDDM-ASR.
+
+Host-side mirror of the reference's interfaces over libfddm_b200.so (include/fddm_b200.h):
+  DiscreteDiffusionScheduler  <- fddm/sched/diffusion_scheduler.py
+  SchedulerAdapter            <- train.py:176-273
+  lfd_loss                    <- losses/fddm_losses.py
+  DiffusionJumpySampler, ModelAdapter <- sampler/jumpy_sampler.py
+There is no CPU path: importing needs the built shared library, ops need CUDA tensors.
+"""
+from . import _lib
+from .scheduler import DiscreteDiffusionScheduler
+from .adapter import SchedulerAdapter
+from .sampler import DiffusionJumpySampler, ModelAdapter
+from .losses import lfd_loss
+
+__all__ = ["DiscreteDiffusionScheduler", "SchedulerAdapter", "DiffusionJumpySampler", "ModelAdapter", "lfd_loss",
+           "_lib"]

@@ -1,0 +1,177 @@
+"""DiffusionJumpySampler / ModelAdapter -- B200 host mirror of sampler/jumpy_sampler.py:54-307.
+
+Same constructor kwargs, attributes, `sample(cond_c, seq_len, init)` and `get_sampling_info()`.
+Each jump is: decoder forward (the caller's module, out of scope) -> ONE fused kernel
+(`fddm_jump_step`: softmax -> Delta-step posterior or alpha-bar mix -> argmax / exponential-race
+resampling, optionally emitting p_x0 and its argmax) preceded in exact mode by the tiny sync-free
+coefficient kernel.  No host synchronisation happens inside `sample`.
+
+Reference quirks that are reproduced on purpose: Q2 exact mode feeds the
+T_infer-axis t to the T_train-length beta table; Q3 fast mode's 0-based/1-based alpha-bar index;
+Q7 any posterior_mode other than "max" goes through `_to_indices`; Q8 `init` is ignored;
+Q9 the ids returned are argmax of the LAST p_x0, the last jump's resampled ids are dropped.
+"""
+from __future__ import annotations
+
+from typing import Literal, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from .scheduler import philox_state
+
+
+class ModelAdapter:
+    """Unifies the denoising decoder as predict_x0_logits(x_t_idx, t, cond_c).  sampler:54-83."""
+
+    def __init__(self, decoder):
+        self.decoder = decoder
+
+    @torch.no_grad()
+    def predict_x0_logits(self, x_t_idx: Tensor, t: Tensor, cond_c: Tensor) -> Tensor:
+        return self.decoder(x_t_idx, t, cond_c)               # positional call, sampler:82
+
+
+class DiffusionJumpySampler:
+    def __init__(self, scheduler, decoder, K: int, T_train: int, T_infer: int, r: int = 2, greedy: bool = True,
+                 posterior_mode: Literal["average", "max"] = "average",
+                 sampling_mode: Literal["exact", "fast"] = "exact", temperature: float = 1.0,
+                 device: Optional[torch.device] = None):
+        self.scheduler = scheduler
+        self.model = ModelAdapter(decoder)
+        self.K = int(K)
+        self.T_train = int(T_train)
+        self.T_infer = int(T_infer)
+        self.r = int(r)
+        self.greedy = bool(greedy)
+        self.posterior_mode = posterior_mode
+        self.sampling_mode = sampling_mode
+        self.temperature = float(temperature)
+        self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        alpha_bar = getattr(self.scheduler, "alpha_bar", None)
+        if alpha_bar is None:                                   # sampler:131-133
+            raise ValueError("scheduler must provide alpha_bar")
+        self.alpha_bar = torch.as_tensor(alpha_bar, dtype=torch.float32, device=self.device)
+        # parity-test hook: callable(step_index, (B, L, K)) -> fp32 Exp(1) noise tensor, or None
+        self.noise_fn = None
+        self.generator: Optional[torch.Generator] = None
+
+    # sampler:219-236, including the 0-based table indexed by a 1-based train-axis index (Q3)
+    def _alpha_bar_index(self, t_infer_scalar: int) -> int:
+        if t_infer_scalar <= 0:
+            return -1                                           # alpha-bar_0 := 1
+        ratio = float(t_infer_scalar) / float(max(1, self.T_infer))
+        t_train_float = max(1.0, min(float(self.T_train), ratio * float(self.T_train)))
+        idx = int(round(t_train_float))
+        if idx >= self.alpha_bar.numel():
+            raise IndexError(f"index {idx} is out of bounds for dimension 0 with size {self.alpha_bar.numel()}")
+        return idx
+
+    def _alpha_bar_at_t_train(self, t_infer_scalar: int) -> Tensor:
+        idx = self._alpha_bar_index(t_infer_scalar)
+        if idx < 0:
+            return torch.tensor(1.0, device=self.device, dtype=torch.float32)
+        return self.alpha_bar[idx]
+
+    @torch.no_grad()
+    def _jump_once(self, x_t_idx: Tensor, t_scalar: int, delta: int, cond_c: Tensor, seq_len: int, *,
+                   want_p: bool = True, step: int = 0) -> Tuple[Tensor, Tensor]:
+        """sampler:167-217.  Returns (x_{t-delta} ids, p_x0).  With want_p=False p_x0 is not
+        materialised (None is returned in its place) -- `sample` only needs the last one."""
+        x_new, p_x0, _ = self._jump(x_t_idx, t_scalar, delta, cond_c, seq_len, want_p=want_p, want_argmax=False,
+                                    step=step)
+        return x_new, p_x0
+
+    def _jump(self, x_t_idx, t_scalar, delta, cond_c, seq_len, *, want_p, want_argmax, step):
+        device = x_t_idx.device
+        B = x_t_idx.size(0)
+        t_tensor = torch.full((B,), t_scalar, device=device, dtype=torch.long)
+        logits = self.model.predict_x0_logits(x_t_idx, t_tensor, cond_c)      # [B, L, K]
+        if logits.dim() != 3 or logits.size(0) != B or logits.size(-1) != self.K:
+            raise ValueError(f"decoder returned logits of shape {tuple(logits.shape)}, expected ({B}, L, {self.K})")
+        Lq = logits.size(1)
+        if Lq != seq_len or tuple(x_t_idx.shape) != (B, Lq):
+            raise ValueError("x_t_idx / logits / seq_len disagree on the sequence length")
+        dev = L.require_cuda(logits, x_t_idx)
+        dt = L.dtype_code(logits)
+        logits = logits.contiguous()
+        x_t = x_t_idx.long().contiguous()
+
+        flags = 0
+        coeffs = None
+        abar_index = -1
+        alpha_bar = None
+        if self.sampling_mode == "exact":
+            flags |= L.JUMP_EXACT
+            # Q2: t on the T_infer axis indexes the scheduler's (T_train-length) beta table as is
+            coeffs = self.scheduler.multistep_coeffs(t_tensor, int(delta))
+            eps = float(self.scheduler.eps)
+        else:
+            abar_index = self._alpha_bar_index(max(0, t_scalar - delta))
+            alpha_bar = self.alpha_bar if self.alpha_bar.device == dev else self.alpha_bar.to(dev)
+            eps = 1e-8
+        sample = (self.posterior_mode != "max") and (not self.greedy)          # sampler:212-215, 153-162
+        noise = None
+        seed = offset = 0
+        if sample:
+            flags |= L.JUMP_SAMPLE
+            if self.noise_fn is not None:
+                noise = self.noise_fn(step, (B, Lq, self.K))
+            if noise is not None:
+                noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+                if noise.numel() != B * Lq * self.K:
+                    raise ValueError("injected noise must have B*L*K elements")
+            else:
+                seed, offset = philox_state(dev, self.generator, 4)
+        p_x0 = None
+        if want_p:
+            flags |= L.JUMP_WRITE_P
+            p_x0 = torch.empty_like(logits)                     # softmax output keeps the logits dtype
+        amax = torch.empty_like(x_t) if want_argmax else None
+        x_out = torch.empty_like(x_t)
+        ws = L.zeroed_workspace(dev, "jump", L.JUMP_WORKSPACE_BYTES)
+        L.check(L.lib.fddm_jump_step(logits.data_ptr(), dt, x_t.data_ptr(), L.ptr(coeffs), L.ptr(alpha_bar),
+                                     abar_index, B, Lq, self.K, flags, self.temperature, eps, L.ptr(noise), seed,
+                                     offset, ws.data_ptr(), x_out.data_ptr(), L.ptr(amax), L.ptr(p_x0),
+                                     L.stream_ptr(dev)), "jump_step")
+        return x_out, p_x0, amax
+
+    @torch.no_grad()
+    def sample(self, cond_c: Tensor, seq_len: int, init: Literal["uniform", "random"] = "uniform"
+               ) -> Tuple[Tensor, Tensor]:
+        """sampler:241-293.  Returns (x_0 ids [B,L], p_x0_last [B,L,K])."""
+        B = cond_c.size(0)
+        device = cond_c.device
+        # both `init` values draw uniform random ids in the reference (Q8, sampler:276-280)
+        x_t_idx = torch.randint(low=0, high=self.K, size=(B, seq_len), device=device, generator=self.generator)
+        t = self.T_infer
+        p_x0_last = None
+        x_0_idx = None
+        step = 0
+        while t > 0:
+            delta = min(self.r, t)
+            last = (t - delta) <= 0
+            # only the last p_x0 is returned, so only the last jump writes it; its argmax (the
+            # sampler's final x_0, sampler:292) is fused into the same kernel
+            x_t_idx, p, amax = self._jump(x_t_idx, t, delta, cond_c, seq_len, want_p=last, want_argmax=last,
+                                          step=step)
+            if last:
+                p_x0_last, x_0_idx = p, amax
+            t -= delta
+            step += 1
+        if p_x0_last is None:                                    # T_infer <= 0: the reference fails here too
+            raise AttributeError("'NoneType' object has no attribute 'argmax'")
+        self.last_resampled_idx = x_t_idx                         # dropped by the reference (Q9); kept for inspection
+        return x_0_idx, p_x0_last
+
+    def get_sampling_info(self) -> dict:
+        return {
+            "sampling_mode": self.sampling_mode,
+            "posterior_mode": self.posterior_mode,
+            "T_infer": self.T_infer,
+            "r": self.r,
+            "greedy": self.greedy,
+            "temperature": self.temperature,
+            "K": self.K,
+        }

@@ -1,0 +1,417 @@
+"""GPU parity tests: the CUDA path (through the C-ABI library, via the host mirror of the reference
+interface) against the reference-generated golden vectors and the numpy oracle on the same seeded
+inputs.  Bars (BASELINE.json north_star): token ids bit-exact under identical injected noise;
+posteriors / losses / gradients within 1e-5 relative in fp32, 1e-2 with bf16 (fp16) inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fddm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+HALF_TOL = 1e-2
+DT = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import fddm_b200
+    assert torch.cuda.is_available()
+    assert fddm_b200._lib.MISSING == []
+    return fddm_b200
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def make_sched(fb, K, T, beta_max=0.2):
+    return fb.DiscreteDiffusionScheduler(K=K, T=T, device=torch.device("cuda"), beta_max=beta_max)
+
+
+def certify_ids(got, want, scores_fn):
+    """ids must be bit-exact; any mismatch has to be a <= 8-ulp near-tie in the oracle's scores."""
+    got = np.asarray(got); want = np.asarray(want)
+    bad = np.argwhere(got != want)
+    for idx in bad:
+        row = scores_fn(tuple(idx))
+        assert O.near_tie(row, int(got[tuple(idx)]), int(want[tuple(idx)])), f"id mismatch at {tuple(idx)} is not a near-tie"
+    return len(bad)
+
+
+# ------------------------------------------------------------------------------------------------
+# tables, q_sample, q_posterior, multi-step posterior
+# ------------------------------------------------------------------------------------------------
+def test_tables_match_reference(fb, golden):
+    s = make_sched(fb, 8000, 200)
+    assert rel_err(s.betas.cpu().numpy(), golden["tab_betas"]) < 1e-6
+    assert rel_err(s.alpha_bar.cpu().numpy(), golden["tab_alpha_bar"]) < 1e-5
+    assert s.w_prefix is s.alpha_bar
+
+
+def test_q_sample_golden(fb, golden):
+    s = make_sched(fb, 8000, 200)
+    ids = golden["qs_x0_ids"]
+    oh = np.zeros(ids.shape + (8000,), np.float32)
+    np.put_along_axis(oh, ids[..., None], 1.0, -1)
+    got = s.q_sample(dev(oh), dev(golden["qs_t"])).cpu().numpy()
+    np.testing.assert_allclose(got, golden["qs_out"], rtol=FP32_TOL, atol=0)
+    np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)            # the reference's sanity check
+    s53 = make_sched(fb, 53, 50, 0.3)
+    got = s53.q_sample(dev(golden["qs53_x0"]), dev(golden["qs53_t"])).cpu().numpy()
+    np.testing.assert_allclose(got, golden["qs53_out"], rtol=FP32_TOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("B,L,K", [(8, 64, 4000), (3, 5, 8000), (2, 3, 32000), (2, 7, 1001)])
+def test_q_sample_and_posteriors_vs_oracle(fb, B, L, K):
+    rng = np.random.default_rng(K + B)
+    T = 200
+    s = make_sched(fb, K, T)
+    betas, abar = s.betas.cpu().numpy(), s.alpha_bar.cpu().numpy()
+    t = rng.integers(1, T + 1, size=B); t[0] = 1; t[-1] = T
+    x0 = rng.dirichlet(np.full(K, 0.05), size=(B, L)).astype(np.float32)
+    xh = O.softmax_lastdim(rng.normal(size=(B, L, K)).astype(np.float32) * 3)
+    got = s.q_sample(dev(x0), dev(t)).cpu().numpy()
+    np.testing.assert_allclose(got, O.q_sample(x0, t, abar), rtol=FP32_TOL, atol=1e-12)
+    xt = got
+    got = s.q_posterior(dev(xt), dev(xh), dev(t)).cpu().numpy()
+    np.testing.assert_allclose(got, O.q_posterior(xt, xh, t, betas), rtol=FP32_TOL, atol=1e-12)
+    np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)
+    for delta in (1, 5, 300):
+        got = s.q_posterior_multi_step(dev(xt), dev(xh), dev(t), delta).cpu().numpy()
+        want = O.q_posterior_multi_step(xt, xh, t, delta, betas, T)
+        np.testing.assert_allclose(got, want, rtol=FP32_TOL, atol=1e-12, err_msg=f"delta={delta}")
+    # delta <= 0 returns xt unchanged (sched:133-134)
+    got = s.q_posterior_multi_step(dev(xt), dev(xh), dev(t), 0).cpu().numpy()
+    assert np.array_equal(got, xt)
+
+
+def test_q_posterior_golden(fb, golden):
+    s = make_sched(fb, 53, 50, 0.3)
+    got = s.q_posterior(dev(golden["qp_xt"]), dev(golden["qp_xh"]), dev(golden["qp_t"])).cpu().numpy()
+    np.testing.assert_allclose(got, golden["qp_out"], rtol=FP32_TOL, atol=1e-12)
+    for ci in range(int(golden["ms_n"])):
+        got = s.q_posterior_multi_step(dev(golden["qp_xt"]), dev(golden["qp_xh"]), dev(golden[f"ms{ci}_t"]),
+                                       int(golden[f"ms{ci}_delta"])).cpu().numpy()
+        np.testing.assert_allclose(got, golden[f"ms{ci}_out"], rtol=FP32_TOL, atol=1e-12, err_msg=f"case {ci}")
+    s8 = make_sched(fb, 8000, 200)
+    xt = np.zeros((3, 1, 8000), np.float32); xt[:, 0, int(golden["ms8k_xt_id"])] = 1
+    for ci in range(3):                                  # the aliased recurrence (quirk Q1) at K=8000
+        got = s8.q_posterior_multi_step(dev(xt), dev(golden["ms8k_xh"]), dev(golden[f"ms8k{ci}_t"]),
+                                        int(golden[f"ms8k{ci}_delta"])).cpu().numpy()
+        np.testing.assert_allclose(got, golden[f"ms8k{ci}_out"], rtol=FP32_TOL, atol=1e-14, err_msg=f"case {ci}")
+
+
+def test_multistep_coeffs_bit_exact(fb):
+    T, K = 200, 8000
+    s = make_sched(fb, K, T)
+    betas = s.betas.cpu().numpy()
+    t = np.array([200, 1, 2, 5, 20, 199, 7], dtype=np.int64)
+    for delta in (1, 2, 5, 7):
+        c = s.multistep_coeffs(dev(t), delta).cpu().numpy()
+        d_eff, a, b, ag, bg = O.multistep_coeffs(t, delta, betas, K, T)
+        B = len(t)
+        assert np.array_equal(c[:B], a) and np.array_equal(c[B:2 * B], b)
+        assert np.array_equal(c[2 * B:3 * B], ag) and np.array_equal(c[3 * B:4 * B], bg)
+        assert c[4 * B] == (1.0 if d_eff <= 0 else 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# sample_q (ids -> ids)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,K,T,bm", [("sq", 8000, 200, 0.2), ("sq53", 53, 50, 0.3)])
+def test_sample_q_ids_golden_bit_exact(fb, golden, tag, K, T, bm):
+    s = make_sched(fb, K, T, bm)
+    ad = fb.SchedulerAdapter(s)
+    x0 = golden[f"{tag}_x0"]
+    got = ad.sample_q(dev(x0), dev(golden[f"{tag}_t"]), exp_noise=dev(golden[f"{tag}_E"])).cpu().numpy()
+    assert got.dtype == np.int64 and got.shape == x0.shape
+    assert np.array_equal(got, golden[f"{tag}_xt"])
+
+
+@pytest.mark.parametrize("B,L,K", [(8, 64, 4000), (4, 16, 8000), (3, 5, 1001)])
+def test_sample_q_ids_vs_oracle(fb, B, L, K):
+    rng = np.random.default_rng(7 * K)
+    T = 200
+    s = make_sched(fb, K, T)
+    abar = s.alpha_bar.cpu().numpy()
+    x0 = rng.integers(0, K, size=(B, L))
+    t = rng.integers(1, T + 1, size=B); t[0] = 1; t[1] = 2; t[-1] = T
+    E = (-np.log1p(-rng.random((B, L, K), dtype=np.float32))).astype(np.float32)
+    E = np.maximum(E, np.float32(1e-30))
+    got = s.sample_q_ids(dev(x0), dev(t), exp_noise=dev(E)).cpu().numpy()
+    want = O.sample_q_ids(x0, t, abar, K, E)
+
+    def scores(idx):
+        oh = np.zeros((1, 1, K), np.float32); oh[0, 0, x0[idx]] = 1
+        return (O.q_sample(oh, t[idx[0]:idx[0] + 1], abar) / E[idx][None, None])[0, 0]
+    assert certify_ids(got, want, scores) == 0
+
+
+def test_sample_q_philox_statistics(fb):
+    """in-kernel Philox path: P(xt == x0) must match alpha_bar_t + (1-alpha_bar_t)/K."""
+    K, T, B, L = 1000, 200, 64, 256
+    s = make_sched(fb, K, T)
+    x0 = torch.randint(0, K, (B, L), device="cuda")
+    t = torch.full((B,), 60, device="cuda", dtype=torch.long)
+    g = torch.Generator(device="cuda"); g.manual_seed(1337)
+    xt = s.sample_q_ids(x0, t, generator=g)
+    xt2 = s.sample_q_ids(x0, t, generator=g)
+    assert not torch.equal(xt, xt2)                            # the generator offset advanced
+    ab = float(s.alpha_bar[59])
+    p_keep = ab + (1 - ab) / K
+    frac = float((xt == x0).float().mean())
+    assert abs(frac - p_keep) < 4 * (p_keep * (1 - p_keep) / (B * L)) ** 0.5 + 1e-3
+    assert int(xt.min()) >= 0 and int(xt.max()) < K
+
+
+# ------------------------------------------------------------------------------------------------
+# diffusion KL (forward + gradient)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,io,K,T,bm", [
+    ("f32", "f32", 53, 50, 0.3), ("f32m", "f32", 53, 50, 0.3), ("bf16m", "bf16", 53, 50, 0.3),
+    ("f16", "f16", 53, 50, 0.3), ("f32k8", "f32", 8000, 200, 0.2)])
+def test_kl_term_golden(fb, golden, tag, io, K, T, bm):
+    s = make_sched(fb, K, T, bm)
+    ad = fb.SchedulerAdapter(s)
+    mask = golden[f"kl_{tag}_mask"]
+    mask = None if mask.size == 0 else dev(mask)
+    logits = dev(golden[f"kl_{tag}_logits"], DT[io]).requires_grad_(True)
+    loss = ad.kl_term(dev(golden[f"kl_{tag}_xt"]), dev(golden[f"kl_{tag}_x0"]), logits, dev(golden[f"kl_{tag}_t"]),
+                      mask)
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    loss.backward()
+    assert logits.grad.dtype == DT[io]
+    tol = FP32_TOL if io == "f32" else HALF_TOL
+    ref = float(golden[f"kl_{tag}_loss"])
+    assert abs(float(loss) - ref) <= tol * abs(ref)
+    assert rel_err(logits.grad.float().cpu().numpy(), golden[f"kl_{tag}_grad"]) < tol
+
+
+def _kl_case(rng, B, L, V, T, sigma):
+    x0 = rng.integers(0, V, size=(B, L))
+    t = rng.integers(1, T + 1, size=B); t[0] = 1; t[1 % B] = 2; t[-1] = T
+    xt = np.where(rng.random((B, L)) < 0.6, x0, rng.integers(0, V, size=(B, L)))
+    logits = (rng.normal(size=(B, L, V)) * sigma).astype(np.float32)
+    lens = rng.integers(0, L + 1, size=B); lens[0] = L
+    if B > 2:
+        lens[2] = 0                                             # an empty sample (quirk Q6)
+    mask = np.arange(L)[None, :] < lens[:, None]
+    return x0, xt, t, logits, mask
+
+
+@pytest.mark.parametrize("io", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("B,L,V,sigma,masked", [
+    (8, 64, 4000, 1.0, True), (4, 9, 8000, 4.0, True), (3, 4, 32000, 1.0, False), (4, 6, 1001, 2.0, True),
+    (2, 3, 16384, 1.0, False), (2, 5, 53, 1.0, True)])
+def test_kl_term_vs_oracle(fb, io, B, L, V, sigma, masked):
+    T = 200
+    rng = np.random.default_rng(V * 3 + B)
+    s = make_sched(fb, V, T)
+    ad = fb.SchedulerAdapter(s)
+    betas = s.betas.cpu().numpy()
+    x0, xt, t, logits, mask = _kl_case(rng, B, L, V, T, sigma)
+    logits = O.round_to_dtype(logits, io)
+    m = mask if masked else None
+    want_loss, want_grad = O.kl_term(xt, x0, logits, t, betas, m, io_dtype=io, dtype=np.float64, want_grad=True)
+    lg = dev(logits, DT[io]).requires_grad_(True)
+    loss = ad.kl_term(dev(xt), dev(x0), lg, dev(t), None if m is None else dev(m))
+    loss.backward()
+    tol = FP32_TOL if io == "f32" else HALF_TOL
+    assert abs(float(loss) - float(want_loss)) <= tol * abs(float(want_loss))
+    assert rel_err(lg.grad.float().cpu().numpy(), want_grad) < tol
+    # forward-only path (no grad) gives the same loss bit for bit, and is deterministic
+    with torch.no_grad():
+        l2 = ad.kl_term(dev(xt), dev(x0), dev(logits, DT[io]), dev(t), None if m is None else dev(m))
+        l3 = ad.kl_term(dev(xt), dev(x0), dev(logits, DT[io]), dev(t), None if m is None else dev(m))
+    assert float(l2) == float(l3)
+    assert abs(float(l2) - float(loss)) <= 1e-6 * abs(float(loss))
+    if masked:                                                  # masked rows get exactly zero gradient
+        g = lg.grad.float().cpu().numpy()
+        assert np.all(g[~mask] == 0)
+
+
+def test_kl_upstream_gradient_scaling(fb):
+    rng = np.random.default_rng(5)
+    B, L, V, T = 4, 8, 4000, 200
+    s = make_sched(fb, V, T)
+    x0, xt, t, logits, mask = _kl_case(rng, B, L, V, T, 1.0)
+    ad = fb.SchedulerAdapter(s)
+    lg = dev(logits).requires_grad_(True)
+    ad.kl_term(dev(xt), dev(x0), lg, dev(t), dev(mask)).backward()
+    base = lg.grad.clone()
+    scale = torch.tensor(1024.0, device="cuda")
+    for adapter in (ad, fb.SchedulerAdapter(s, grad_scale=scale)):       # rescale pass vs folded-in hint
+        lg2 = dev(logits).requires_grad_(True)
+        (adapter.kl_term(dev(xt), dev(x0), lg2, dev(t), dev(mask)) * scale).backward()
+        assert rel_err(lg2.grad.cpu().numpy(), (base * 1024.0).cpu().numpy()) < 1e-6
+
+
+def test_kl_validation_loss_call_pattern(fb):
+    """evaluate.py:228-233 calls kl_term(xt=x0, x0, logits, t=1, mask) under no_grad."""
+    rng = np.random.default_rng(11)
+    B, L, V, T = 4, 16, 8000, 200
+    s = make_sched(fb, V, T)
+    x0 = rng.integers(0, V, size=(B, L)); t = np.ones(B, dtype=np.int64)
+    logits = rng.normal(size=(B, L, V)).astype(np.float32)
+    mask = x0 != 0
+    want, _ = O.kl_term(x0, x0, logits, t, s.betas.cpu().numpy(), mask, dtype=np.float64)
+    with torch.no_grad():
+        got = fb.SchedulerAdapter(s).kl_term(dev(x0), dev(x0), dev(logits), dev(t), dev(mask))
+    assert abs(float(got) - float(want)) <= FP32_TOL * abs(float(want))
+
+
+def test_errors_are_loud(fb):
+    s = make_sched(fb, 100, 50)
+    ad = fb.SchedulerAdapter(s)
+    with pytest.raises(ValueError):                              # CPU tensors: no CPU fallback
+        ad.kl_term(torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, 3, dtype=torch.long),
+                   torch.zeros(2, 3, 100), torch.ones(2, dtype=torch.long))
+    with pytest.raises(AssertionError):                          # K mismatch (sched:42)
+        s.q_sample(torch.zeros(2, 3, 99, device="cuda"), torch.ones(2, dtype=torch.long, device="cuda"))
+    with pytest.raises(TypeError):
+        ad.kl_term(torch.zeros(2, 3, dtype=torch.long, device="cuda"), torch.zeros(2, 3, dtype=torch.long, device="cuda"),
+                   torch.zeros(2, 3, 100, device="cuda", dtype=torch.float64), torch.ones(2, dtype=torch.long, device="cuda"))
+    big = fb.DiscreteDiffusionScheduler(K=60000, T=10, device=torch.device("cuda"))
+    with pytest.raises(fb._lib.FddmError):                       # beyond FDDM_MAX_VOCAB
+        fb.SchedulerAdapter(big).kl_term(torch.zeros(1, 1, dtype=torch.long, device="cuda"),
+                                         torch.zeros(1, 1, dtype=torch.long, device="cuda"),
+                                         torch.zeros(1, 1, 60000, device="cuda"),
+                                         torch.ones(1, dtype=torch.long, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------
+# jumpy sampler
+# ------------------------------------------------------------------------------------------------
+SAMPLER_TAGS = ["ex_g", "ex_s", "ex_map", "ex_max", "fa_g", "fa_s", "fa_st", "ex_st", "ex_s_bf16", "fa_g_bf16",
+                "ex_s_8k"]
+
+
+class ReplayDecoder:
+    """Stands in for the denoising decoder (out of scope): returns pre-generated logits per jump and
+    records the ids / t it was called with."""
+
+    def __init__(self, logits, dtype):
+        self.logits = [dev(l, dtype) for l in logits]
+        self.seen_x, self.seen_t = [], []
+
+    def __call__(self, x, t, c):
+        self.seen_x.append(x.cpu().numpy().copy()); self.seen_t.append(t.cpu().numpy().copy())
+        return self.logits[len(self.seen_x) - 1]
+
+
+@pytest.mark.parametrize("tag", SAMPLER_TAGS)
+def test_jumpy_sampler_golden_chain(fb, golden, tag, monkeypatch):
+    K, T_train, T_infer, r, B, L, greedy = [int(v) for v in golden[f"js_{tag}_cfg"]]
+    mode, pmode, temp, dt = [str(s) for s in golden[f"js_{tag}_mode"]]
+    tdt = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16, "torch.float16": torch.float16}[dt]
+    s = make_sched(fb, K, T_train, 0.2 if K == 8000 else 0.3)
+    dec = ReplayDecoder(golden[f"js_{tag}_logits"], tdt)
+    smp = fb.DiffusionJumpySampler(s, dec, K=K, T_train=T_train, T_infer=T_infer, r=r, greedy=bool(greedy),
+                                   posterior_mode=pmode, sampling_mode=mode, temperature=float(temp),
+                                   device=torch.device("cuda"))
+    noise = golden[f"js_{tag}_noise"]
+    if noise.size:
+        smp.noise_fn = lambda step, shape: dev(noise[step].reshape(shape))
+    xT = dev(golden[f"js_{tag}_xT"])
+    monkeypatch.setattr(torch, "randint", lambda *a, **k: xT)          # the reference draws x_T with randint
+    x0, p_last = smp.sample(torch.zeros(B, 1, 1, device="cuda"), L)
+    seen = np.stack(dec.seen_x)
+    want_seen = golden[f"js_{tag}_x_seen"]
+    # ids fed to the decoder at every jump == the reference's, bit for bit (half dtypes: near-ties allowed)
+    if tdt == torch.float32:
+        assert np.array_equal(seen, want_seen)
+        assert np.array_equal(x0.cpu().numpy(), golden[f"js_{tag}_x0"])
+    else:
+        assert (seen != want_seen).mean() <= 0.05
+    assert np.array_equal(np.stack(dec.seen_t), golden[f"js_{tag}_t_seen"])
+    assert p_last.dtype == tdt and str(golden[f"js_{tag}_p_last_dtype"]) == dt
+    tol = FP32_TOL if tdt == torch.float32 else HALF_TOL
+    if np.array_equal(seen, want_seen):
+        np.testing.assert_allclose(p_last.float().cpu().numpy(), golden[f"js_{tag}_p_last"], rtol=tol, atol=1e-30)
+    info = smp.get_sampling_info()
+    assert info["sampling_mode"] == mode and info["K"] == K and info["r"] == r
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("greedy,temp", [(True, 1.0), (False, 1.0), (False, 0.7)])
+@pytest.mark.parametrize("B,L,K", [(4, 8, 8000), (3, 5, 1001), (2, 4, 32000)])
+def test_jump_step_vs_oracle(fb, mode, greedy, temp, B, L, K):
+    T_train, T_infer, r = 200, 20, 5
+    rng = np.random.default_rng(K + B + int(greedy))
+    s = make_sched(fb, K, T_train)
+    betas, abar = s.betas.cpu().numpy(), s.alpha_bar.cpu().numpy()
+    for t_scalar in (20, 5):
+        delta = min(r, t_scalar)
+        logits = (rng.normal(size=(B, L, K)) * 3).astype(np.float32)
+        x_t = rng.integers(0, K, size=(B, L))
+        E = np.maximum((-np.log1p(-rng.random((B, L, K), dtype=np.float32))).astype(np.float32), np.float32(1e-30))
+        dec = ReplayDecoder([logits], torch.float32)
+        smp = fb.DiffusionJumpySampler(s, dec, K=K, T_train=T_train, T_infer=T_infer, r=r, greedy=greedy,
+                                       sampling_mode=mode, temperature=temp, device=torch.device("cuda"))
+        smp.noise_fn = lambda step, shape: dev(E)
+        ids, p_x0 = smp._jump_once(dev(x_t), t_scalar, delta, torch.zeros(B, 1, 1, device="cuda"), L)
+        want_ids, want_p, p_post = O.jump_once(x_t, logits, t_scalar, delta, K=K, T_train=T_train, T_infer=T_infer,
+                                               betas=betas, alpha_bar=abar, sampling_mode=mode, greedy=greedy,
+                                               temperature=temp, exp_noise=E)
+        np.testing.assert_allclose(p_x0.cpu().numpy(), want_p, rtol=FP32_TOL, atol=1e-30)
+
+        def scores(idx):
+            p = p_post[idx]
+            if greedy:
+                return p
+            if temp != 1.0:
+                p = O.softmax_lastdim(np.log(np.maximum(p, np.float32(1e-12))) / np.float32(temp))
+            return (p / p.sum(dtype=np.float32)) / E[idx]
+        nbad = certify_ids(ids.cpu().numpy(), want_ids, scores)
+        assert nbad <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# L_fd
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["r0", "r9", "l1"])
+def test_lfd_golden(fb, golden, tag):
+    za = dev(golden[f"lfd_{tag}_za"]).requires_grad_(True)
+    zb = dev(golden[f"lfd_{tag}_zb"]).requires_grad_(True)
+    loss = fb.lfd_loss(za, zb, float(golden[f"lfd_{tag}_lam"]))
+    loss.backward()
+    ref = float(golden[f"lfd_{tag}_loss"])
+    assert loss.dtype == torch.float32
+    assert abs(float(loss) - ref) <= FP32_TOL * abs(ref)
+    assert rel_err(za.grad.cpu().numpy(), golden[f"lfd_{tag}_ga"]) < 2e-5
+    assert rel_err(zb.grad.cpu().numpy(), golden[f"lfd_{tag}_gb"]) < 2e-5
+
+
+@pytest.mark.parametrize("io", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("B,T,D,rho", [(32, 128, 768, 0.0), (32, 128, 768, 0.9), (16, 37, 256, 0.9), (4, 130, 264, 0.5),
+                                       (8, 5, 16, 0.9)])
+def test_lfd_vs_oracle(fb, io, B, T, D, rho):
+    rng = np.random.default_rng(D + T)
+    za = (rng.normal(size=(B, T, D)) * 1.7 + 0.3).astype(np.float32)
+    zb = (rho * (za - 0.3) / 1.7 + np.sqrt(1 - rho * rho) * rng.normal(size=(B, T, D))).astype(np.float32) * 0.5 - 1.0
+    za, zb = O.round_to_dtype(za, io), O.round_to_dtype(zb, io)
+    lam = 5e-3
+    want, ga, gb = O.lfd_loss(za, zb, lam, dtype=np.float64, want_grad=True)
+    a = dev(za, DT[io]).requires_grad_(True); b = dev(zb, DT[io]).requires_grad_(True)
+    loss = fb.lfd_loss(a, b, lam)
+    assert loss.dtype == DT[io]                                   # result in the input dtype (survey a8)
+    (loss.float() * 3.0).backward()
+    tol = FP32_TOL if io == "f32" else HALF_TOL
+    assert abs(float(loss) - float(want)) <= tol * abs(float(want))
+    gtol = 2e-5 if io == "f32" else HALF_TOL
+    assert rel_err(a.grad.float().cpu().numpy(), 3.0 * ga) < gtol
+    assert rel_err(b.grad.float().cpu().numpy(), 3.0 * gb) < gtol
+
+
+def test_lfd_shape_assert(fb):
+    with pytest.raises(AssertionError):
+        fb.lfd_loss(torch.zeros(2, 3, 8, device="cuda"), torch.zeros(2, 3, 16, device="cuda"))

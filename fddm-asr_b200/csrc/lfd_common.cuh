@@ -22,12 +22,13 @@ struct LfdWorkspace {
   static constexpr size_t kCounters = 256;            // self-resetting unsigned counters
   static constexpr size_t kMaxPartials = 1024;        // loss partial sums (double)
   static constexpr int kMaxSplits = 148;
-  size_t off_partials, off_tables, off_splitk, off_dza, off_dzb, total;
+  size_t off_partials, off_diag, off_tables, off_splitk, off_dza, off_dzb, total;
   __host__ __device__ LfdWorkspace(int64_t B, int64_t T, int64_t D) {
     const size_t td = static_cast<size_t>(T) * D, rows = static_cast<size_t>(B) * T;
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     off_partials = kCounters;
-    off_tables = al(off_partials + kMaxPartials * sizeof(double));
+    off_diag = al(off_partials + kMaxPartials * sizeof(double));          // exact fp64 diagonal of cov
+    off_tables = al(off_diag + static_cast<size_t>(D) * sizeof(double));
     off_splitk = al(off_tables + 4 * td * sizeof(float));               // a_scale a_shift b_scale b_shift
     off_dza = al(off_splitk + static_cast<size_t>(kMaxSplits) * D * D * sizeof(float));
     off_dzb = al(off_dza + rows * D * sizeof(float));

@@ -87,11 +87,59 @@ __global__ void __launch_bounds__(256) lfd_tables_kernel(const double* __restric
   tables[which * 2 * TD + TD + j] = static_cast<float>(-mean * rstd);
 }
 
-// cov[i] = sum_s partial[s][i], fixed order (deterministic split-K reduction)
+// The diagonal of cov on the CUDA cores with fp64 accumulation: diag[j] += sum_rows za~[r,j] zb~[r,j].
+// Why: the tensor-core accumulator adds with truncation, harmless for the zero-mean off-diagonal
+// sums but a systematic ~1e-6 relative bias on the all-positive diagonal sums when z_a and z_b are
+// correlated -- and the loss is dominated by sum_j (1-C_jj)^2.  One more read of the inputs (s bytes
+// per element), D results.  grid = (ceil(D/N/64), row slices); rows are strided over blockIdx.y.
+template <typename T>
+__global__ void __launch_bounds__(256) lfd_diag_kernel(const T* __restrict__ za, const T* __restrict__ zb,
+                                                       const float* __restrict__ tables, int64_t rows, int Tn, int D,
+                                                       double* __restrict__ diag) {
+  constexpr int N = Vec16<T>::N;
+  __shared__ double s_acc[4][64][N];
+  const int vx = threadIdx.x & 63, ry = threadIdx.x >> 6;       // 64 d-vectors x 4 row lanes per CTA
+  const int v = blockIdx.x * 64 + vx;
+  const int64_t TD = static_cast<int64_t>(Tn) * D;
+  double acc[N];
+#pragma unroll
+  for (int e = 0; e < N; ++e) acc[e] = 0.0;
+  if (v * N < D) {
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 4 + ry; r < rows; r += static_cast<int64_t>(gridDim.y) * 4) {
+      const int64_t so = (r % Tn) * D + v * N;
+      float a[N], b[N];
+      Vec16<T>::unpack(ldg_stream_v4(za + r * D + v * N), a);
+      Vec16<T>::unpack(ldg_stream_v4(zb + r * D + v * N), b);
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float at = fmaf(a[e], tables[so + e], tables[TD + so + e]);
+        const float bt = fmaf(b[e], tables[2 * TD + so + e], tables[3 * TD + so + e]);
+        acc[e] += static_cast<double>(at) * static_cast<double>(bt);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < N; ++e) s_acc[ry][vx][e] = acc[e];
+  __syncthreads();
+  if (ry == 0 && v * N < D) {
+#pragma unroll
+    for (int e = 0; e < N; ++e)
+      atomicAdd(diag + v * N + e, (s_acc[0][vx][e] + s_acc[1][vx][e]) + (s_acc[2][vx][e] + s_acc[3][vx][e]));
+  }
+}
+
+// cov[i] = sum_s partial[s][i], fixed order (deterministic split-K reduction); the diagonal comes
+// from the fp64 CUDA-core sums
 __global__ void __launch_bounds__(256) lfd_splitk_reduce_kernel(const float* __restrict__ partial, int splits,
-                                                                int64_t n, float* __restrict__ cov) {
+                                                                int64_t n, int D, const double* __restrict__ diag,
+                                                                float* __restrict__ cov) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t j = i / D;
+    if (i - j * D == j) {
+      cov[i] = static_cast<float>(diag[j]);
+      continue;
+    }
     float a = 0.0f;
     for (int s = 0; s < splits; ++s) a += partial[static_cast<int64_t>(s) * n + i];
     cov[i] = a;
@@ -360,6 +408,8 @@ int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_common("lfd_xcov", z_a, z_b, dtype, B, T, D)) return rc;
   FDDM_CHECK_ARG(sums && workspace && cov, "lfd_xcov: null pointer argument");
+  FDDM_CHECK_ARG(reinterpret_cast<uintptr_t>(z_a) % 16 == 0 && reinterpret_cast<uintptr_t>(z_b) % 16 == 0,
+                 "lfd_xcov: inputs must be 16-byte aligned");
   FDDM_CHECK_ARG(n_batch_global >= static_cast<double>(B), "lfd_xcov: n_batch_global < B");
   if (D % 8 != 0) {
     set_error("lfd_xcov: D=%lld must be a multiple of 8 for the tensor-core contraction", (long long)D);
@@ -381,9 +431,28 @@ int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_
   const int splits = pick_splits(tiles, rows);
   const int terms = (dtype == FDDM_BF16) ? 1 : 2;
   if (int rc = umma_gemm(A, Bo, D, D, rows, splits, terms, 1.0f, partial, D, D * D, stream)) return rc;
+  double* diag = reinterpret_cast<double*>(ws + lay.off_diag);
+  FDDM_CUDA_OK(cudaMemsetAsync(diag, 0, sizeof(double) * D, stream));
+  {
+    const int nvec = static_cast<int>(D / (dtype == FDDM_F32 ? 4 : 8));
+    const int gx = (nvec + 63) / 64;
+    const int gy = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + 3) / 4, (num_sms() * 8 + gx - 1) / gx)));
+    dim3 grid(gx, gy, 1);
+    if (dtype == FDDM_F32)
+      lfd_diag_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(z_a), static_cast<const float*>(z_b),
+                                                       tables, rows, static_cast<int>(T), static_cast<int>(D), diag);
+    else if (dtype == FDDM_BF16)
+      lfd_diag_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z_a),
+                                                               static_cast<const __nv_bfloat16*>(z_b), tables, rows,
+                                                               static_cast<int>(T), static_cast<int>(D), diag);
+    else
+      lfd_diag_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(z_a), static_cast<const __half*>(z_b),
+                                                        tables, rows, static_cast<int>(T), static_cast<int>(D), diag);
+    FDDM_LAUNCH_OK();
+  }
   const int64_t n = D * D;
   lfd_splitk_reduce_kernel<<<static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, num_sms() * 8)), 256, 0,
-                             stream>>>(partial, splits, n, cov);
+                             stream>>>(partial, splits, n, static_cast<int>(D), diag, cov);
   FDDM_LAUNCH_OK();
   return FDDM_OK;
 }

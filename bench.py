@@ -250,12 +250,12 @@ def run_gpu(args):
         return float(tt.item())
 
     # ---- device-resident throughput (`value`) ----------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                                            # samples cover warm-up + both timed regions
     for _ in range(args.warmup):
         step(d)
     sync_all()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     n0 = fb._lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -304,11 +304,14 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel: fused KL forward+backward (2*s bytes per element) ------
     peak, peak_src = peaks()
-    algo_bytes = 2.0 * s_bytes * elems
+    # logits of masked rows are never read (their gradient rows are still written): count what the
+    # algorithm must move -- read s bytes per element of the valid rows, write s bytes per element of all rows
+    valid_rows = int(host["mask"].sum())
+    algo_bytes = float(s_bytes) * V * (valid_rows + B * L)
     achieved = algo_bytes / (kl_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "kl_rows_ring_kernel (fused KL forward+backward)", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                "algorithmic_bytes_per_launch": algo_bytes, "ms_per_launch": round(kl_ms, 4), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "valid_row_fraction": round(valid_rows / (B * L), 4), "ms_per_launch": round(kl_ms, 4), "peak_source": peak_src,
                 "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
 
     cpu = None

@@ -87,45 +87,118 @@ __global__ void __launch_bounds__(256) lfd_tables_kernel(const double* __restric
   tables[which * 2 * TD + TD + j] = static_cast<float>(-mean * rstd);
 }
 
-// The diagonal of cov on the CUDA cores with fp64 accumulation: diag[j] += sum_rows za~[r,j] zb~[r,j].
-// Why: the tensor-core accumulator adds with truncation, harmless for the zero-mean off-diagonal
-// sums but a systematic ~1e-6 relative bias on the all-positive diagonal sums when z_a and z_b are
-// correlated -- and the loss is dominated by sum_j (1-C_jj)^2.  One more read of the inputs (s bytes
-// per element), D results.  grid = (ceil(D/N/64), row slices); rows are strided over blockIdx.y.
+// One pass over z_a and z_b: standardise (losses:23-26), split into bf16 hi + residual, write the
+// packed tensor-core operand planes P[c/8][r][c%8] (lfd_common.cuh), zero the padding, and accumulate
+// the diagonal of cov in fp64:  diag[j] += sum_rows za~[r,j] zb~[r,j].
+// Why the diagonal is done here on the CUDA cores: the tensor-core accumulator adds with truncation,
+// harmless for the zero-mean off-diagonal sums but a systematic ~1e-6 relative bias on the all-positive
+// diagonal sums when z_a and z_b are correlated -- and the loss is dominated by sum_j (1-C_jj)^2.
+// Mapping: warp -> chunk column (8 channels), lanes -> 32 consecutive rows: each lane reads 32 (16)
+// contiguous bytes of its row (whole sectors), the warp writes 512 contiguous bytes per plane.
+// grid = (D_pad/64, R_pad/256), 8 warps per CTA.
 template <typename T>
-__global__ void __launch_bounds__(256) lfd_diag_kernel(const T* __restrict__ za, const T* __restrict__ zb,
+__global__ void __launch_bounds__(256) lfd_pack_kernel(const T* __restrict__ za, const T* __restrict__ zb,
                                                        const float* __restrict__ tables, int64_t rows, int Tn, int D,
-                                                       double* __restrict__ diag) {
-  constexpr int N = Vec16<T>::N;
-  __shared__ double s_acc[4][64][N];
-  const int vx = threadIdx.x & 63, ry = threadIdx.x >> 6;       // 64 d-vectors x 4 row lanes per CTA
-  const int v = blockIdx.x * 64 + vx;
+                                                       int64_t R_pad, __nv_bfloat16* __restrict__ a_hi,
+                                                       __nv_bfloat16* __restrict__ a_lo, __nv_bfloat16* __restrict__ b_hi,
+                                                       __nv_bfloat16* __restrict__ b_lo, double* __restrict__ diag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cc = blockIdx.x * 8 + warp;                      // chunk column
+  const int c0 = cc * 8;
   const int64_t TD = static_cast<int64_t>(Tn) * D;
-  double acc[N];
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.y) * 256;
+  double acc[8];
 #pragma unroll
-  for (int e = 0; e < N; ++e) acc[e] = 0.0;
-  if (v * N < D) {
-    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 4 + ry; r < rows; r += static_cast<int64_t>(gridDim.y) * 4) {
-      const int64_t so = (r % Tn) * D + v * N;
-      float a[N], b[N];
-      Vec16<T>::unpack(ldg_stream_v4(za + r * D + v * N), a);
-      Vec16<T>::unpack(ldg_stream_v4(zb + r * D + v * N), b);
-#pragma unroll
-      for (int e = 0; e < N; ++e) {
-        const float at = fmaf(a[e], tables[so + e], tables[TD + so + e]);
-        const float bt = fmaf(b[e], tables[2 * TD + so + e], tables[3 * TD + so + e]);
-        acc[e] += static_cast<double>(at) * static_cast<double>(bt);
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+  const bool col_ok = c0 < D;
+#pragma unroll 2
+  for (int it = 0; it < 8; ++it) {
+    const int64_t r = r_begin + it * 32 + lane;
+    float a[8], b[8];
+    if (col_ok && r < rows) {
+      if (sizeof(T) == 4) {
+        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(za) + r * D + c0), a);
+        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(za) + r * D + c0 + 4), a + 4);
+        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(zb) + r * D + c0), b);
+        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(zb) + r * D + c0 + 4), b + 4);
+      } else {
+        Vec16<T>::unpack(ldg_stream_v4(za + r * D + c0), a);
+        Vec16<T>::unpack(ldg_stream_v4(zb + r * D + c0), b);
       }
+      const int64_t so = (r % Tn) * D + c0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 sa = __ldg(reinterpret_cast<const float4*>(tables + so) + h);
+        const float4 ha = __ldg(reinterpret_cast<const float4*>(tables + TD + so) + h);
+        const float4 sb = __ldg(reinterpret_cast<const float4*>(tables + 2 * TD + so) + h);
+        const float4 hb = __ldg(reinterpret_cast<const float4*>(tables + 3 * TD + so) + h);
+        a[4 * h + 0] = fmaf(a[4 * h + 0], sa.x, ha.x); a[4 * h + 1] = fmaf(a[4 * h + 1], sa.y, ha.y);
+        a[4 * h + 2] = fmaf(a[4 * h + 2], sa.z, ha.z); a[4 * h + 3] = fmaf(a[4 * h + 3], sa.w, ha.w);
+        b[4 * h + 0] = fmaf(b[4 * h + 0], sb.x, hb.x); b[4 * h + 1] = fmaf(b[4 * h + 1], sb.y, hb.y);
+        b[4 * h + 2] = fmaf(b[4 * h + 2], sb.z, hb.z); b[4 * h + 3] = fmaf(b[4 * h + 3], sb.w, hb.w);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += static_cast<double>(a[e]) * static_cast<double>(b[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] = 0.0f; b[e] = 0.0f; }
+    }
+    const int64_t off = (static_cast<int64_t>(cc) * R_pad + r) * 8;       // elements
+    const uint4 ah = Vec16<__nv_bfloat16>::pack(a), bh = Vec16<__nv_bfloat16>::pack(b);
+    stg_stream_v4(a_hi + off, ah);
+    stg_stream_v4(b_hi + off, bh);
+    if (a_lo != nullptr) {
+      float t[8];
+      Vec16<__nv_bfloat16>::unpack(ah, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = a[e] - t[e];                     // exact in fp32
+      stg_stream_v4(a_lo + off, Vec16<__nv_bfloat16>::pack(t));
+      Vec16<__nv_bfloat16>::unpack(bh, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = b[e] - t[e];
+      stg_stream_v4(b_lo + off, Vec16<__nv_bfloat16>::pack(t));
     }
   }
+  if (col_ok) {
 #pragma unroll
-  for (int e = 0; e < N; ++e) s_acc[ry][vx][e] = acc[e];
-  __syncthreads();
-  if (ry == 0 && v * N < D) {
+    for (int e = 0; e < 8; ++e) {
+      double v = acc[e];
 #pragma unroll
-    for (int e = 0; e < N; ++e)
-      atomicAdd(diag + v * N + e, (s_acc[0][vx][e] + s_acc[1][vx][e]) + (s_acc[2][vx][e] + s_acc[3][vx][e]));
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(diag + c0 + e, v);
+    }
   }
+}
+
+// G (fp32 [D][D]) -> packed hi/lo planes of G and of G^T, zero padded to D_pad.
+// thread = (chunk column cc, row r); lanes run over r.  grid = (D_pad/8, D_pad/256).
+__global__ void __launch_bounds__(256) lfd_pack_g_kernel(const float* __restrict__ G, int D, int64_t D_pad,
+                                                         __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo,
+                                                         __nv_bfloat16* __restrict__ gt_hi,
+                                                         __nv_bfloat16* __restrict__ gt_lo) {
+  const int cc = blockIdx.x, c0 = cc * 8;
+  const int64_t r = static_cast<int64_t>(blockIdx.y) * 256 + threadIdx.x;
+  float g[8], gt[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const bool ok = r < D && c0 + e < D;
+    g[e] = ok ? G[r * D + c0 + e] : 0.0f;               // P(G):   X[r][c] = G[r][c]
+    gt[e] = ok ? G[static_cast<int64_t>(c0 + e) * D + r] : 0.0f;   // P(G^T): X[r][c] = G[c][r]
+  }
+  const int64_t off = (static_cast<int64_t>(cc) * D_pad + r) * 8;
+  float t[8];
+  uint4 h = Vec16<__nv_bfloat16>::pack(g);
+  *reinterpret_cast<uint4*>(g_hi + off) = h;
+  Vec16<__nv_bfloat16>::unpack(h, t);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) t[e] = g[e] - t[e];
+  *reinterpret_cast<uint4*>(g_lo + off) = Vec16<__nv_bfloat16>::pack(t);
+  h = Vec16<__nv_bfloat16>::pack(gt);
+  *reinterpret_cast<uint4*>(gt_hi + off) = h;
+  Vec16<__nv_bfloat16>::unpack(h, t);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) t[e] = gt[e] - t[e];
+  *reinterpret_cast<uint4*>(gt_lo + off) = Vec16<__nv_bfloat16>::pack(t);
 }
 
 // cov[i] = sum_s partial[s][i], fixed order (deterministic split-K reduction); the diagonal comes
@@ -383,6 +456,59 @@ int pick_splits(int64_t tiles, int64_t rows) {
   return static_cast<int>(s);
 }
 
+
+int check_gemm_shape(const char* what, const void* za, const void* zb, int64_t D) {
+  if (D % 8 != 0) {
+    set_error("%s: D=%lld must be a multiple of 8 for the tensor-core contraction", what, (long long)D);
+    return FDDM_EUNSUPPORTED;
+  }
+  FDDM_CHECK_ARG(reinterpret_cast<uintptr_t>(za) % 16 == 0 && reinterpret_cast<uintptr_t>(zb) % 16 == 0,
+                 "%s: inputs must be 16-byte aligned", what);
+  return FDDM_OK;
+}
+
+// tables + the one-pass standardise / split / pack (+ fp64 diagonal)
+int standardise_and_pack(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D,
+                         const double* sums, double n_batch_global, float eps, uint8_t* ws, const LfdWorkspace& lay,
+                         int terms, cudaStream_t stream) {
+  float* tables = reinterpret_cast<float*>(ws + lay.off_tables);
+  double* diag = reinterpret_cast<double*>(ws + lay.off_diag);
+  const int64_t TD = T * D, rows = B * T, Rp = pack_pad(rows), Dp = pack_pad(D);
+  if (int rc = launch_tables(sums, TD, n_batch_global, eps, tables, stream)) return rc;
+  FDDM_CUDA_OK(cudaMemsetAsync(diag, 0, sizeof(double) * D, stream));
+  __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_pack);
+  const size_t pe = lay.plane_bytes / 2;
+  __nv_bfloat16 *a_hi = pl, *a_lo = terms == 2 ? pl + pe : nullptr, *b_hi = pl + 2 * pe,
+                *b_lo = terms == 2 ? pl + 3 * pe : nullptr;
+  dim3 grid(static_cast<unsigned>(Dp / 64), static_cast<unsigned>(Rp / 256));
+  if (dtype == FDDM_F32)
+    lfd_pack_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(z_a), static_cast<const float*>(z_b),
+                                                     tables, rows, static_cast<int>(T), static_cast<int>(D), Rp, a_hi,
+                                                     a_lo, b_hi, b_lo, diag);
+  else if (dtype == FDDM_BF16)
+    lfd_pack_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z_a),
+                                                             static_cast<const __nv_bfloat16*>(z_b), tables, rows,
+                                                             static_cast<int>(T), static_cast<int>(D), Rp, a_hi, a_lo,
+                                                             b_hi, b_lo, diag);
+  else
+    lfd_pack_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(z_a), static_cast<const __half*>(z_b),
+                                                      tables, rows, static_cast<int>(T), static_cast<int>(D), Rp, a_hi,
+                                                      a_lo, b_hi, b_lo, diag);
+  FDDM_LAUNCH_OK();
+  return FDDM_OK;
+}
+
+void planes_of(uint8_t* ws, const LfdWorkspace& lay, int64_t B, int64_t T, int64_t D, int terms, int mn_is_col,
+               PackedOperand& A, PackedOperand& Bo) {
+  __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_pack);
+  const size_t pe = lay.plane_bytes / 2;
+  A.hi = pl; A.lo = terms == 2 ? pl + pe : nullptr;
+  Bo.hi = pl + 2 * pe; Bo.lo = terms == 2 ? pl + 3 * pe : nullptr;
+  A.R_pad = Bo.R_pad = pack_pad(B * T);
+  A.C_pad = Bo.C_pad = pack_pad(D);
+  A.mn_is_col = Bo.mn_is_col = mn_is_col;
+}
+
 }  // namespace
 }  // namespace fddm
 
@@ -408,51 +534,24 @@ int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_common("lfd_xcov", z_a, z_b, dtype, B, T, D)) return rc;
   FDDM_CHECK_ARG(sums && workspace && cov, "lfd_xcov: null pointer argument");
-  FDDM_CHECK_ARG(reinterpret_cast<uintptr_t>(z_a) % 16 == 0 && reinterpret_cast<uintptr_t>(z_b) % 16 == 0,
-                 "lfd_xcov: inputs must be 16-byte aligned");
   FDDM_CHECK_ARG(n_batch_global >= static_cast<double>(B), "lfd_xcov: n_batch_global < B");
-  if (D % 8 != 0) {
-    set_error("lfd_xcov: D=%lld must be a multiple of 8 for the tensor-core contraction", (long long)D);
-    return FDDM_EUNSUPPORTED;
-  }
+  if (int rc = check_gemm_shape("lfd_xcov", z_a, z_b, D)) return rc;
   const LfdWorkspace lay(B, T, D);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* tables = reinterpret_cast<float*>(ws + lay.off_tables);
   float* partial = reinterpret_cast<float*>(ws + lay.off_splitk);
-  const int64_t TD = T * D, rows = B * T;
-  if (int rc = launch_tables(sums, TD, n_batch_global, eps, tables, stream)) return rc;
-
-  UmmaOperand A{}, Bo{};
-  A.ptr = z_a; A.dtype = dtype; A.ld = D; A.nrows = rows; A.ncols = D; A.mn_is_col = 1;
-  A.scale = tables; A.shift = tables + TD; A.T = static_cast<int>(T); A.stat_ld = D;
-  Bo = A;
-  Bo.ptr = z_b; Bo.scale = tables + 2 * TD; Bo.shift = tables + 3 * TD;
+  const int64_t rows = B * T;
+  const int terms = (dtype == FDDM_BF16) ? 1 : 2;       // bf16 inputs: the reference's matmul operands are bf16 too
+  if (int rc = standardise_and_pack(z_a, z_b, dtype, B, T, D, sums, n_batch_global, eps, ws, lay, terms, stream))
+    return rc;
+  PackedOperand A{}, Bo{};
+  planes_of(ws, lay, B, T, D, terms, 1, A, Bo);
   const int64_t tiles = ((D + 127) / 128) * ((D + 255) / 256);
   const int splits = pick_splits(tiles, rows);
-  const int terms = (dtype == FDDM_BF16) ? 1 : 2;
   if (int rc = umma_gemm(A, Bo, D, D, rows, splits, terms, 1.0f, partial, D, D * D, stream)) return rc;
-  double* diag = reinterpret_cast<double*>(ws + lay.off_diag);
-  FDDM_CUDA_OK(cudaMemsetAsync(diag, 0, sizeof(double) * D, stream));
-  {
-    const int nvec = static_cast<int>(D / (dtype == FDDM_F32 ? 4 : 8));
-    const int gx = (nvec + 63) / 64;
-    const int gy = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + 3) / 4, (num_sms() * 8 + gx - 1) / gx)));
-    dim3 grid(gx, gy, 1);
-    if (dtype == FDDM_F32)
-      lfd_diag_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(z_a), static_cast<const float*>(z_b),
-                                                       tables, rows, static_cast<int>(T), static_cast<int>(D), diag);
-    else if (dtype == FDDM_BF16)
-      lfd_diag_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z_a),
-                                                               static_cast<const __nv_bfloat16*>(z_b), tables, rows,
-                                                               static_cast<int>(T), static_cast<int>(D), diag);
-    else
-      lfd_diag_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(z_a), static_cast<const __half*>(z_b),
-                                                        tables, rows, static_cast<int>(T), static_cast<int>(D), diag);
-    FDDM_LAUNCH_OK();
-  }
   const int64_t n = D * D;
   lfd_splitk_reduce_kernel<<<static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, num_sms() * 8)), 256, 0,
-                             stream>>>(partial, splits, n, static_cast<int>(D), diag, cov);
+                             stream>>>(partial, splits, n, static_cast<int>(D),
+                                       reinterpret_cast<const double*>(ws + lay.off_diag), cov);
   FDDM_LAUNCH_OK();
   return FDDM_OK;
 }
@@ -480,11 +579,10 @@ int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, in
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_common("lfd_backward", z_a, z_b, dtype, B, T, D)) return rc;
   FDDM_CHECK_ARG(sums && G && workspace && bn_sums && dz_a && dz_b, "lfd_backward: null pointer argument");
+  const bool planes_valid = (phase & FDDM_LFD_PLANES_VALID) != 0;
+  phase &= ~FDDM_LFD_PLANES_VALID;
   FDDM_CHECK_ARG(phase == 0 || phase == 1, "lfd_backward: phase must be 0 or 1");
-  if (D % 8 != 0) {
-    set_error("lfd_backward: D=%lld must be a multiple of 8 for the tensor-core contraction", (long long)D);
-    return FDDM_EUNSUPPORTED;
-  }
+  if (int rc = check_gemm_shape("lfd_backward", z_a, z_b, D)) return rc;
   const LfdWorkspace lay(B, T, D);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* tables = reinterpret_cast<float*>(ws + lay.off_tables);
@@ -492,22 +590,27 @@ int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, in
   float* dzb = reinterpret_cast<float*>(ws + lay.off_dzb);
   const int64_t TD = T * D, rows = B * T;
   if (phase == 0) {
-    // tables are recomputed here: another lfd call may have reused the workspace since the forward
-    if (int rc = launch_tables(sums, TD, n_batch_global, eps, tables, stream)) return rc;
-    const int terms = 2;          // G is fp32: keep hi + residual for every input dtype
+    // the forward's tables / planes are reused only when the caller vouches that this workspace still
+    // holds them; the backward always needs the residual planes (G is fp32: hi + residual for all dtypes)
+    const bool have_lo = (dtype != FDDM_BF16);
+    if (!planes_valid || !have_lo)
+      if (int rc = standardise_and_pack(z_a, z_b, dtype, B, T, D, sums, n_batch_global, eps, ws, lay, 2, stream))
+        return rc;
+    const int64_t Dp = pack_pad(D);
+    __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_gpack);
+    const size_t ge = lay.gplane_bytes / 2;
+    lfd_pack_g_kernel<<<dim3(static_cast<unsigned>(Dp / 8), static_cast<unsigned>(Dp / 256)), 256, 0, stream>>>(
+        G, static_cast<int>(D), Dp, gp, gp + ge, gp + 2 * ge, gp + 3 * ge);
+    FDDM_LAUNCH_OK();
     const float alpha = static_cast<float>(1.0 / n_rows_global);
-    UmmaOperand Za{}, Zb{}, Gk{}, Gmn{};
-    Za.ptr = z_a; Za.dtype = dtype; Za.ld = D; Za.nrows = rows; Za.ncols = D; Za.mn_is_col = 0;
-    Za.scale = tables; Za.shift = tables + TD; Za.T = static_cast<int>(T); Za.stat_ld = D;
-    Zb = Za;
-    Zb.ptr = z_b; Zb.scale = tables + 2 * TD; Zb.shift = tables + 3 * TD;
-    Gk.ptr = G; Gk.dtype = FDDM_F32; Gk.ld = D; Gk.nrows = D; Gk.ncols = D; Gk.mn_is_col = 0;   // B(n=j, k) = G[j][k]
-    Gk.scale = nullptr; Gk.shift = nullptr; Gk.T = 1; Gk.stat_ld = 0;
-    Gmn = Gk; Gmn.mn_is_col = 1;                                                                // B(n=k, j) = G[j][k]
+    PackedOperand Za{}, Zb{}, Gk{}, Gt{};
+    planes_of(ws, lay, B, T, D, 2, 0, Za, Zb);
+    Gk.hi = gp; Gk.lo = gp + ge; Gk.R_pad = Dp; Gk.C_pad = Dp; Gk.mn_is_col = 0;            // B(n=j, k) = G[j][k]
+    Gt = Gk; Gt.hi = gp + 2 * ge; Gt.lo = gp + 3 * ge;                                      // B(n=k, j) = G^T[k][j]
     // dza~[r][j] = (1/N) sum_k zb~[r][k] G[j][k]          (oracle: B2 @ G.T / N)
-    if (int rc = umma_gemm(Zb, Gk, rows, D, D, 1, terms, alpha, dza, D, 0, stream)) return rc;
+    if (int rc = umma_gemm(Zb, Gk, rows, D, D, 1, 2, alpha, dza, D, 0, stream)) return rc;
     // dzb~[r][k] = (1/N) sum_j za~[r][j] G[j][k]          (oracle: A2 @ G / N)
-    if (int rc = umma_gemm(Za, Gmn, rows, D, D, 1, terms, alpha, dzb, D, 0, stream)) return rc;
+    if (int rc = umma_gemm(Za, Gt, rows, D, D, 1, 2, alpha, dzb, D, 0, stream)) return rc;
     return FDDM_DISPATCH_DT(dtype, launch_bn, z_a, z_b, dtype, B, TD, dza, dzb, tables, bn_sums, stream);
   }
   return FDDM_DISPATCH_DT(dtype, launch_finalize, z_a, z_b, dtype, B, TD, dza, dzb, tables, bn_sums,

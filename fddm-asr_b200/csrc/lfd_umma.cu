@@ -2,28 +2,22 @@
 //
 //   out[s][m][n] = alpha * sum_{k in split s} A(m,k) * B(n,k)          fp32 accumulation in TMEM
 //
-// Operands are row-major global matrices that are *transformed on the way into shared memory*: each
-// producer thread loads 8 contiguous elements (one 16-byte bf16 chunk after conversion), applies the
-// per-(position, channel) standardisation x~ = x*rstd - mean*rstd of losses/fddm_losses.py:23-26,
-// splits the fp32 value into bf16 hi + bf16 residual (so that hi*hi + hi*lo + lo*hi carries ~16
-// mantissa bits through the bf16 tensor pipe; 1e-5 parity needs more than TF32's 10) and stores both
-// into UMMA's canonical no-swizzle layout.  So z_a / z_b are read once per tile straight from
-// HBM/L2 -- no standardised copy is ever materialised -- and no TMA tensor map is involved.
+// Operands arrive in the packed bf16 (hi, lo) planes described in lfd_common.cuh: every run of rows of
+// one 8-column chunk is already a column of UMMA core matrices, so a pipeline stage is filled by a
+// handful of 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier:
 //
-// Shared-memory operand tile (per term): R rows x C columns of the global matrix (C contiguous),
-// stored as 16-byte chunks:   chunk(cc, r)  at  cc*CS + (r/8)*128 + (r%8)*16,  CS = (R/8)*128 + 32.
-// A "core matrix" = 8 rows x 16 bytes = 128 contiguous bytes.  The +32 pad makes the producers'
-// stores conflict-free (a quarter-warp writes 4 chunk-columns x 2 rows = 8 distinct 16-byte slots)
-// while their global loads stay row-contiguous (4 lanes x 32 B = one 128-byte line per row).
-//   * operand read "down the rows" (MN index = column, K index = row; the forward's z~^T z~):
-//     MN-major descriptor, SBO (stride between 8-element MN chunks) = CS, LBO (between 8-row K groups) = 128
-//   * operand read "along the rows" (MN index = row, K index = column; the backward's z~ G):
-//     K-major descriptor, SBO (between 8-row MN groups) = 128, LBO (between 8-element K chunks) = CS
+//   warp 0      producer: lane 0 arms full[s] with the stage's byte count, all 32 lanes issue copies
+//   warp 1      MMA issuer: one elected lane, tcgen05.mma cta_group::1 kind::f16, M=128, N<=256, K=16;
+//               tcgen05.commit -> empty[s] frees the stage, the last commit signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 16 columns) TMEM -> registers -> global
 //
-// CTA = 8 producer/epilogue warps + 1 MMA warp.  mbarrier ring: producers -> full[s] (256 arrivals
-// after fence.proxy.async) -> one elected thread issues tcgen05.mma kind::f16 (M=128, N<=256, K=16)
-// -> tcgen05.commit -> empty[s].  The last commit signals the epilogue, which reads the 128 x N
-// fp32 accumulator out of TMEM with tcgen05.ld (32 lanes x 16 columns per instruction).
+// fp32 accuracy: hi*hi + hi*lo + lo*hi (three MMAs per K step) carries ~16 mantissa bits through the
+// bf16 pipe; 1e-5 parity on correlated inputs needs more than TF32's 10.
+//
+// Shared-memory tile (one plane, dense): chunk column cc, row r at  cc*(R*16) + r*16  (R = rows in the
+// tile), i.e. 8-row x 16-byte core matrices of 128 contiguous bytes.
+//   MN index = column (forward):  R = BK rows;  MN-major descriptor, SBO = BK*16, LBO = 128
+//   MN index = row    (backward): R = TM rows;  K-major descriptor,  SBO = 128,   LBO = TM*16
 #include <algorithm>
 
 #include "lfd_common.cuh"
@@ -34,21 +28,15 @@ namespace {
 constexpr int kBM = 128;              // UMMA M (TMEM lanes)
 constexpr int kBK = 32;               // K extent of one pipeline stage (two K=16 MMAs per term pair)
 constexpr int kMaxBN = 256;
-constexpr int kProducerWarps = 8;
-constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = kProducerThreads + 32;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kTmemCols = 256;
-constexpr int kMaxStages = 6;
-
-__host__ __device__ constexpr uint32_t chunk_stride(int R) { return static_cast<uint32_t>(R / 8) * 128u + 32u; }
-// bytes of one operand tile (one term) for either orientation, upper bound over both
-constexpr uint32_t kTileA = 16 * chunk_stride(kBK);       // MN-major: 128/8 chunk columns of 32 rows = 8704
-constexpr uint32_t kTileB = 32 * chunk_stride(kBK);       // 256/8 chunk columns                      = 17408
-static_assert(4 * chunk_stride(kBM) <= kTileA, "K-major A tile must fit");
-static_assert(4 * chunk_stride(kMaxBN) <= kTileB, "K-major B tile must fit");
+constexpr int kMaxStages = 8;
+constexpr uint32_t kTileA = kBM * kBK * 2;       // bytes of one A plane per stage (8192)
+constexpr uint32_t kTileB = kMaxBN * kBK * 2;    // bytes of one B plane per stage (16384)
 
 struct GemmParams {
-  UmmaOperand A, B;
+  PackedOperand A, B;
   int M, N, K;
   int BN;                 // UMMA N of this launch (multiple of 32, <= 256)
   int tiles_m, tiles_n, splits;
@@ -101,65 +89,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// ---- producer: one operand tile, global -> registers -> (standardise, split) -> shared ---------
-template <int TERMS>
-__device__ __forceinline__ void load_operand_tile(const UmmaOperand& op, int64_t mn0, int mn_extent, int64_t k0,
-                                                  int64_t k_end, uint8_t* s_hi, uint8_t* s_lo, int warp, int lane) {
-  const int R = op.mn_is_col ? kBK : mn_extent;
-  const int C = op.mn_is_col ? mn_extent : kBK;
-  const int64_t row0 = op.mn_is_col ? k0 : mn0;
-  const int64_t col0 = op.mn_is_col ? mn0 : k0;
-  const int64_t row_end = op.mn_is_col ? min(op.nrows, k_end) : op.nrows;
-  const int64_t col_end = op.mn_is_col ? op.ncols : min(op.ncols, k_end);
-  const uint32_t CS = chunk_stride(R);
-  const int ncb = C / 32;                        // 32-column blocks (4 chunks) across the tile
-  const int nwb = ncb * (R / 8);                 // warp-blocks: 8 rows x 4 chunks
-  for (int wb = warp; wb < nwb; wb += kProducerWarps) {
-    const int cb = wb % ncb, rb = wb / ncb;
-    const int cc = cb * 4 + (lane & 3);
-    const int r = rb * 8 + (lane >> 2);
-    const int64_t gr = row0 + r, gc = col0 + static_cast<int64_t>(cc) * 8;
-    float x[8];
-    if (gr < row_end && gc < col_end) {          // extents are multiples of 8 columns: all-or-nothing
-      if (op.dtype == FDDM_F32) {
-        const float* p = static_cast<const float*>(op.ptr) + gr * op.ld + gc;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-      } else if (op.dtype == FDDM_BF16) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(op.ptr) + gr * op.ld + gc));
-        Vec16<__nv_bfloat16>::unpack(v, x);
-      } else {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(op.ptr) + gr * op.ld + gc));
-        Vec16<__half>::unpack(v, x);
-      }
-      if (op.scale != nullptr) {
-        const int64_t so = (gr % op.T) * op.stat_ld + gc;
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(op.scale + so));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(op.scale + so) + 1);
-        const float4 h0 = __ldg(reinterpret_cast<const float4*>(op.shift + so));
-        const float4 h1 = __ldg(reinterpret_cast<const float4*>(op.shift + so) + 1);
-        x[0] = fmaf(x[0], s0.x, h0.x); x[1] = fmaf(x[1], s0.y, h0.y);
-        x[2] = fmaf(x[2], s0.z, h0.z); x[3] = fmaf(x[3], s0.w, h0.w);
-        x[4] = fmaf(x[4], s1.x, h1.x); x[5] = fmaf(x[5], s1.y, h1.y);
-        x[6] = fmaf(x[6], s1.z, h1.z); x[7] = fmaf(x[7], s1.w, h1.w);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = 0.0f;
-    }
-    const uint32_t off = static_cast<uint32_t>(cc) * CS + static_cast<uint32_t>(r >> 3) * 128u +
-                         static_cast<uint32_t>(r & 7) * 16u;
-    const uint4 hi = Vec16<__nv_bfloat16>::pack(x);
-    *reinterpret_cast<uint4*>(s_hi + off) = hi;
-    if (TERMS == 2) {
-      float h[8];
-      Vec16<__nv_bfloat16>::unpack(hi, h);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = x[e] - h[e];          // exact in fp32
-      *reinterpret_cast<uint4*>(s_lo + off) = Vec16<__nv_bfloat16>::pack(h);
-    }
+// number of bulk copies / bytes per copy that fill one plane of an operand tile
+struct TilePlan {
+  int ncopies;
+  uint32_t bytes;          // per copy
+  int64_t src_stride;      // elements between consecutive copies in the packed plane
+  int64_t src_base;        // element offset of copy 0 for (mn0, k0)
+};
+__device__ __forceinline__ TilePlan plan_tile(const PackedOperand& op, int64_t mn0, int mn_extent, int64_t k0) {
+  TilePlan t;
+  if (op.mn_is_col) {      // chunk columns along MN, rows along K
+    t.ncopies = mn_extent / 8;
+    t.bytes = kBK * 16;
+    t.src_stride = op.R_pad * 8;
+    t.src_base = ((mn0 / 8) * op.R_pad + k0) * 8;
+  } else {                 // chunk columns along K, rows along MN
+    t.ncopies = kBK / 8;
+    t.bytes = static_cast<uint32_t>(mn_extent) * 16;
+    t.src_stride = op.R_pad * 8;
+    t.src_base = ((k0 / 8) * op.R_pad + mn0) * 8;
   }
+  return t;
 }
 
 template <int TERMS>
@@ -178,17 +128,17 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
   const int64_t m0 = static_cast<int64_t>(tm) * kBM, n0 = static_cast<int64_t>(tn) * p.BN;
   const int64_t k_begin = static_cast<int64_t>(split) * p.k_per_split;
   const int64_t k_end = min(static_cast<int64_t>(p.K), k_begin + p.k_per_split);
-  const int num_kb = static_cast<int>((k_end - k_begin + kBK - 1) / kBK);
+  const int num_kb = static_cast<int>((k_end - k_begin + kBK - 1) / kBK);   // padded planes hold zeros past K
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&s_full[s], kProducerThreads);
+      mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 1);
     }
     mbar_init(&s_accum, 1);
     mbar_fence_init();
   }
-  if (warp == kProducerWarps) {                      // the MMA warp owns the TMEM allocation
+  if (warp == 1) {                                   // the MMA warp owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                  "r"(static_cast<uint32_t>(kTmemCols))
                  : "memory");
@@ -199,54 +149,40 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
   tc_fence_after();
   const uint32_t tmem_d = s_tmem_base;
 
-  if (warp < kProducerWarps) {
-    // ===== producers =====
+  if (warp == 0) {
+    // ===== producer: 1-D TMA bulk copies of packed core-matrix columns =====
+    const uint32_t bytesA = kBM * kBK * 2, bytesB = static_cast<uint32_t>(p.BN) * kBK * 2;
+    const uint32_t tx = TERMS * (bytesA + bytesB);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % p.stages;
       const uint32_t round = static_cast<uint32_t>(kb / p.stages);
       if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1);
+      if (lane == 0) mbar_arrive_expect_tx(&s_full[s], tx);
+      __syncwarp();
       uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-      uint8_t* a_hi = st;
-      uint8_t* a_lo = st + kTileA;                   // only with TERMS == 2
-      uint8_t* b_hi = st + TERMS * kTileA;
-      uint8_t* b_lo = b_hi + kTileB;
       const int64_t k0 = k_begin + static_cast<int64_t>(kb) * kBK;
-      load_operand_tile<TERMS>(p.A, m0, kBM, k0, k_end, a_hi, a_lo, warp, lane);
-      load_operand_tile<TERMS>(p.B, n0, p.BN, k0, k_end, b_hi, b_lo, warp, lane);
-      fence_proxy_async();                           // generic-proxy stores -> visible to the MMA (async proxy)
-      mbar_arrive(&s_full[s]);
-    }
-    // ===== epilogue: TMEM -> registers -> global =====
-    mbar_wait(&s_accum, 0);
-    tc_fence_after();
-    const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int64_t m = m0 + q * 32 + lane;
-    float* orow = p.out + static_cast<int64_t>(split) * p.out_split_stride + m * p.out_ld;
-    for (int c = (warp >> 2) * 16; c < p.BN; c += 32) {
-      float v[16];
-      tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
-      const int64_t n = n0 + c;
-      if (m < p.M && n < p.N) {                      // N is a multiple of 8; handle the 16-column chunk in halves
+      const TilePlan ta = plan_tile(p.A, m0, kBM, k0), tb = plan_tile(p.B, n0, p.BN, k0);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          if (n + 4 * h < p.N) {
-            float4 o = make_float4(v[4 * h] * p.alpha, v[4 * h + 1] * p.alpha, v[4 * h + 2] * p.alpha,
-                                   v[4 * h + 3] * p.alpha);
-            *reinterpret_cast<float4*>(orow + n + 4 * h) = o;
-          }
-        }
+      for (int term = 0; term < TERMS; ++term) {
+        const __nv_bfloat16* pa = term == 0 ? p.A.hi : p.A.lo;
+        const __nv_bfloat16* pb = term == 0 ? p.B.hi : p.B.lo;
+        uint8_t* da = st + term * kTileA;
+        uint8_t* db = st + TERMS * kTileA + term * kTileB;
+        for (int c = lane; c < ta.ncopies; c += 32)
+          tma_load_1d(da + static_cast<size_t>(c) * ta.bytes, pa + ta.src_base + c * ta.src_stride, ta.bytes, &s_full[s]);
+        for (int c = lane; c < tb.ncopies; c += 32)
+          tma_load_1d(db + static_cast<size_t>(c) * tb.bytes, pb + tb.src_base + c * tb.src_stride, tb.bytes, &s_full[s]);
       }
     }
-    tc_fence_before();
-  } else {
+  } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
       const uint32_t idesc = make_instr_desc(p.A.mn_is_col, p.B.mn_is_col, p.BN);
-      const uint32_t csA = chunk_stride(p.A.mn_is_col ? kBK : kBM);
-      const uint32_t csB = chunk_stride(p.B.mn_is_col ? kBK : p.BN);
+      const uint32_t csA = p.A.mn_is_col ? kBK * 16u : kBM * 16u;          // bytes between chunk columns
+      const uint32_t csB = p.B.mn_is_col ? kBK * 16u : static_cast<uint32_t>(p.BN) * 16u;
       const uint32_t lboA = p.A.mn_is_col ? 128u : csA, sboA = p.A.mn_is_col ? csA : 128u;
       const uint32_t lboB = p.B.mn_is_col ? 128u : csB, sboB = p.B.mn_is_col ? csB : 128u;
-      const uint32_t advA = p.A.mn_is_col ? 256u : 2u * csA;     // K += 16 within a stage
+      const uint32_t advA = p.A.mn_is_col ? 256u : 2u * csA;               // K += 16 within a stage
       const uint32_t advB = p.B.mn_is_col ? 256u : 2u * csB;
       uint32_t accum = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -258,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
         const uint32_t a_hi = st, a_lo = st + kTileA, b_hi = st + TERMS * kTileA, b_lo = b_hi + kTileB;
 #pragma unroll
         for (int term = 0; term < (TERMS == 2 ? 3 : 1); ++term) {
-          const uint32_t a_base = (term == 2) ? a_lo : a_hi;     // hi*hi, hi*lo, lo*hi
+          const uint32_t a_base = (term == 2) ? a_lo : a_hi;               // hi*hi, hi*lo, lo*hi
           const uint32_t b_base = (term == 1) ? b_lo : b_hi;
 #pragma unroll
           for (int ks = 0; ks < kBK / 16; ++ks) {
@@ -273,9 +209,32 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
       umma_commit(&s_accum);                         // accumulator complete
     }
     __syncwarp();
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(&s_accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp id % 4)
+    const int64_t m = m0 + q * 32 + lane;
+    float* orow = p.out + static_cast<int64_t>(split) * p.out_split_stride + m * p.out_ld;
+    for (int c = 0; c < p.BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+      const int64_t n = n0 + c;
+      if (m < p.M && n < p.N) {                      // N is a multiple of 4: 16-byte stores
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (n + 4 * h < p.N) {
+            float4 o = make_float4(v[4 * h] * p.alpha, v[4 * h + 1] * p.alpha, v[4 * h + 2] * p.alpha,
+                                   v[4 * h + 3] * p.alpha);
+            *reinterpret_cast<float4*>(orow + n + 4 * h) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
   }
   __syncthreads();
-  if (warp == kProducerWarps) {
+  if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
                  "r"(static_cast<uint32_t>(kTmemCols))
@@ -283,21 +242,24 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
   }
 }
 
-bool operand_ok(const UmmaOperand& o) {
-  return o.ptr && reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0 && o.ld % 8 == 0 && o.ncols % 8 == 0 &&
-         (o.scale == nullptr || (o.shift != nullptr && reinterpret_cast<uintptr_t>(o.scale) % 16 == 0 &&
-                                 reinterpret_cast<uintptr_t>(o.shift) % 16 == 0 && o.stat_ld % 4 == 0 && o.T > 0));
+bool operand_ok(const PackedOperand& o, int terms) {
+  return o.hi && (terms == 1 || o.lo) && reinterpret_cast<uintptr_t>(o.hi) % 16 == 0 &&
+         reinterpret_cast<uintptr_t>(o.lo) % 16 == 0 && o.R_pad % kPackPad == 0 && o.C_pad % kPackPad == 0;
 }
 
 }  // namespace
 
-int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, int64_t M, int64_t N, int64_t K, int splits, int terms,
+int umma_gemm(const PackedOperand& A, const PackedOperand& B, int64_t M, int64_t N, int64_t K, int splits, int terms,
               float alpha, float* out, int64_t out_ld, int64_t out_split_stride, cudaStream_t stream) {
-  FDDM_CHECK_ARG(operand_ok(A) && operand_ok(B), "umma_gemm: operand alignment (16-byte pointers, ld %% 8 == 0)");
-  FDDM_CHECK_ARG(M > 0 && N > 0 && K > 0 && splits >= 1 && (terms == 1 || terms == 2), "umma_gemm: bad shape");
+  FDDM_CHECK_ARG(terms == 1 || terms == 2, "umma_gemm: terms must be 1 or 2");
+  FDDM_CHECK_ARG(operand_ok(A, terms) && operand_ok(B, terms), "umma_gemm: packed operand alignment / padding");
+  FDDM_CHECK_ARG(M > 0 && N > 0 && K > 0 && splits >= 1, "umma_gemm: bad shape");
   FDDM_CHECK_ARG(out && reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_ld % 4 == 0 && N % 4 == 0 &&
                      out_split_stride % 4 == 0,
                  "umma_gemm: output alignment");
+  // padded extents must cover every tile the grid touches
+  const int64_t mA = A.mn_is_col ? A.C_pad : A.R_pad, kA = A.mn_is_col ? A.R_pad : A.C_pad;
+  const int64_t nB = B.mn_is_col ? B.C_pad : B.R_pad, kB = B.mn_is_col ? B.R_pad : B.C_pad;
   GemmParams p;
   p.A = A; p.B = B;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
@@ -309,6 +271,10 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, int64_t M, int64_t N, 
   p.k_per_split = static_cast<int>(kps);
   p.splits = static_cast<int>((K + kps - 1) / kps);         // every split owns >= 1 k-block
   FDDM_CHECK_ARG(p.splits <= splits, "umma_gemm: internal split error");
+  const int64_t k_cover = (K + kBK - 1) / kBK * kBK;
+  FDDM_CHECK_ARG(static_cast<int64_t>(p.tiles_m) * kBM <= mA && static_cast<int64_t>(p.tiles_n) * p.BN <= nB &&
+                     k_cover <= kA && k_cover <= kB,
+                 "umma_gemm: packed planes do not cover the tile grid");
   p.terms = terms;
   const uint32_t stage_bytes = static_cast<uint32_t>(terms) * (kTileA + kTileB);
   p.stages = std::min<int>(kMaxStages, static_cast<int>((200u * 1024u) / stage_bytes));

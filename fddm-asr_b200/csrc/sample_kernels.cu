@@ -15,6 +15,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "rowkit.cuh"
 
@@ -165,6 +166,30 @@ __global__ void __launch_bounds__(NT) sample_q_kernel(const SampleQParams p) {
   }
 }
 
+
+// In-kernel RNG path: for a one-hot x0 the categorical q(x_t|x_0) has two values, so a draw needs O(1)
+// work per token instead of a race over all K entries: keep x0 with probability p_hi, otherwise pick
+// one of the other K-1 ids uniformly.  Same distribution as torch.multinomial on the q_sample row
+// (the per-entry race is only needed to replay *injected* noise bit for bit, see sample_q_kernel).
+__global__ void __launch_bounds__(256) sample_q_closed_kernel(const SampleQParams p) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= p.rows) return;
+  long long tt = p.t[row / p.L];
+  tt = tt < 1 ? 1 : (tt > p.T ? p.T : tt);
+  float p_hi, p_lo;
+  q_sample_two_values(p.alpha_bar[tt - 1], p.u, p.eps, p.K, p_hi, p_lo);
+  const int x0 = static_cast<int>(p.x0[row]);
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(row), 0u, p.off.x, p.off.y), p.key);
+  const float u1 = static_cast<float>(r.x >> 8) * (1.0f / 16777216.0f);             // [0,1)
+  int out = x0;
+  if (!(u1 < p_hi) && p.K > 1) {
+    // uniform over the K-1 other ids: 32 random bits scaled by (K-1) without modulo bias worth noting
+    int j = static_cast<int>(__umulhi(r.y, static_cast<uint32_t>(p.K - 1)));
+    out = j + (j >= x0 ? 1 : 0);
+  }
+  p.out[row] = out;
+}
+
 #endif  // !FDDM_JUMP_DT
 
 // ------------------------------------------------------------------------------------------------
@@ -267,39 +292,72 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
       const float v = value(k, xh);
       if (v > best) { best = v; best_k = k; }
     });
-  } else if (p.temperature == 1.0f) {
-    for_each_noise(row, nz, [&](int k, float& xh, float E) {
-      const float sc = __fdiv_rn(value(k, xh), E);
-      if (sc > best) { best = sc; best_k = k; }
-    });
   } else {
-    // temperature path (sampler:159-161): probs = softmax(log(clamp(p_norm, 1e-12)) / tau).
-    // exact mode needs the normalised posterior (sched:200-204); fast mode uses the mix as is.
-    float scale = 1.0f, dn = 1.0f;
-    if (exact) {
-      // denom = a*x0hat[xt] + b*sum_xh*sum_xt ; x0hat[xt] is held by exactly one thread
-      float d1[1] = {0.0f};
-      row.for_each([&](int k, float& xh) { if (k == c.xt) d1[0] = xh; });
-      block_sum<NT, 1>(d1, red);
-      dn = fmaxf(__fadd_rn(__fmul_rn(c.a_c, d1[0]), __fmul_rn(c.b_c, sum_xh)), p.eps);
-      float ps[1] = {0.0f};
-      row.for_each([&](int k, float& xh) { ps[0] += __fdiv_rn(value(k, xh), dn); });
-      block_sum<NT, 1>(ps, red);
-      scale = fmaxf(ps[0], p.eps);
-    }
+    // Categorical weights w_k: the un-normalised target distribution, or with a temperature
+    // (sampler:159-161) softmax(log(clamp(p_norm, 1e-12)) / tau) evaluated as exp(logit - max).
+    const bool temp = (p.temperature != 1.0f);
+    float scale = 1.0f, dn = 1.0f, m2 = 0.0f;
     const float inv_tau = 1.0f / p.temperature;
     auto logit_of = [&](int k, float xh) -> float {
       float pn = value(k, xh);
       if (exact) pn = __fdiv_rn(__fdiv_rn(pn, dn), scale);
       return logf(fmaxf(pn, 1e-12f)) * inv_tau;
     };
-    float m2 = kNegInf;
-    row.for_each([&](int k, float& xh) { m2 = fmaxf(m2, logit_of(k, xh)); });
-    m2 = block_max<NT>(m2, red);
-    for_each_noise(row, nz, [&](int k, float& xh, float E) {
-      const float sc = __fdiv_rn(expf(logit_of(k, xh) - m2), E);
-      if (sc > best) { best = sc; best_k = k; }
-    });
+    if (temp) {
+      if (exact) {
+        // exact mode needs the normalised posterior (sched:200-204):
+        // denom = a*x0hat[xt] + b*sum_xh*sum_xt ; x0hat[xt] is held by exactly one thread
+        float d1[1] = {0.0f};
+        row.for_each([&](int k, float& xh) { if (k == c.xt) d1[0] = xh; });
+        block_sum<NT, 1>(d1, red);
+        dn = fmaxf(__fadd_rn(__fmul_rn(c.a_c, d1[0]), __fmul_rn(c.b_c, sum_xh)), p.eps);
+        float ps[1] = {0.0f};
+        row.for_each([&](int k, float& xh) { ps[0] += __fdiv_rn(value(k, xh), dn); });
+        block_sum<NT, 1>(ps, red);
+        scale = fmaxf(ps[0], p.eps);
+      }
+      m2 = kNegInf;
+      row.for_each([&](int k, float& xh) { m2 = fmaxf(m2, logit_of(k, xh)); });
+      m2 = block_max<NT>(m2, red);
+    }
+    auto weight = [&](int k, float xh) -> float { return temp ? expf(logit_of(k, xh) - m2) : value(k, xh); };
+    if constexpr (std::is_same<NoiseT, NoisePhilox>::value) {
+      // In-kernel RNG: hierarchical exponential race.  The minimum of independent exponentials with
+      // rates w_k is Exp(sum w_k) and its argmin is categorical in w_k, independent of the minimum;
+      // so each thread races once with its local mass (one Exp(1) variate per thread instead of
+      // one per vocab entry) and the winning thread picks among its own entries by inverse CDF.
+      float mass = 0.0f;
+      row.for_each([&](int k, float& xh) { mass += weight(k, xh); });
+      const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(row.tid), nz.row, nz.off.x, nz.off.y), nz.key);
+      best = __fdividef(mass, exp1_from_bits(rnd.x));
+      best_k = row.tid;
+      block_argmax<NT>(best, best_k, red);
+      int* pick = reinterpret_cast<int*>(red) + 64;
+      if (row.tid == best_k) {
+        const float target = mass * ((static_cast<float>(rnd.y >> 8) + 1.0f) * (1.0f / 16777216.0f));
+        float cum = 0.0f;
+        int chosen = -1, last_pos = c.xt;
+        row.for_each([&](int k, float& xh) {
+          const float w = weight(k, xh);
+          if (chosen < 0 && w > 0.0f) {
+            cum += w;
+            last_pos = k;
+            if (cum >= target) chosen = k;
+          }
+        });
+        *pick = (chosen < 0) ? last_pos : chosen;
+      }
+      consumer_sync<NT>();
+      const int res = *pick;
+      consumer_sync<NT>();
+      return res;
+    } else {
+      // injected noise: the reference's per-entry race argmax_k w_k / E_k, bit for bit
+      for_each_noise(row, nz, [&](int k, float& xh, float E) {
+        const float sc = __fdiv_rn(weight(k, xh), E);
+        if (sc > best) { best = sc; best_k = k; }
+      });
+    }
   }
   block_argmax<NT>(best, best_k, red);
   return best_k;
@@ -539,9 +597,12 @@ int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_ba
   p.u = static_cast<float>(1.0 / static_cast<double>(K));
   p.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   p.off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
-  const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(num_sms()) * 8));
-  if (exp_noise) sample_q_kernel<256, false><<<grid, 256, 0, stream>>>(p);
-  else sample_q_kernel<256, true><<<grid, 256, 0, stream>>>(p);
+  if (exp_noise) {
+    const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(num_sms()) * 8));
+    sample_q_kernel<256, false><<<grid, 256, 0, stream>>>(p);
+  } else {
+    sample_q_closed_kernel<<<(p.rows + 255) / 256, 256, 0, stream>>>(p);
+  }
   FDDM_LAUNCH_OK();
   return FDDM_OK;
 }

@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("FDDM_B200_LIB") or os.path.join(os.path.dirname(_HERE
 F32, BF16, F16 = 0, 1, 2
 JUMP_EXACT, JUMP_SAMPLE, JUMP_WRITE_P = 0x1, 0x2, 0x4
 JUMP_WORKSPACE_BYTES = 128
+LFD_PLANES_VALID = 0x2
 MAX_VOCAB = 49152
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}

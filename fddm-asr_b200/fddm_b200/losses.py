@@ -30,7 +30,14 @@ class _LfdFn(torch.autograd.Function):
         dt = L.dtype_code(z_a)
         world = 1 if group is None else torch.distributed.get_world_size(group)
         st = L.stream_ptr(dev)
-        ws = L.zeroed_workspace(dev, "lfd", int(L.lib.fddm_lfd_workspace_bytes(B, T, D)))
+        nbytes = int(L.lib.fddm_lfd_workspace_bytes(B, T, D))
+        if any(ctx.needs_input_grad[:2]):
+            # a workspace of its own, kept until backward: the packed tensor-core operand planes and the
+            # standardisation tables written by the forward are reused by the backward contractions
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws[:256].zero_()
+        else:
+            ws = L.zeroed_workspace(dev, "lfd", nbytes)
         sums = torch.empty(4 * T * D, dtype=torch.float64, device=dev)
         L.check(L.lib.fddm_lfd_stats(z_a.data_ptr(), z_b.data_ptr(), dt, B, T, D, sums.data_ptr(), st), "lfd_stats")
         _all_reduce(sums, group)
@@ -42,24 +49,24 @@ class _LfdFn(torch.autograd.Function):
         G = torch.empty(D * D, dtype=torch.float32, device=dev)
         L.check(L.lib.fddm_lfd_loss(cov.data_ptr(), D, float(B * T * world), float(lambda_offdiag), ws.data_ptr(),
                                     loss.data_ptr(), G.data_ptr(), st), "lfd_loss")
-        ctx.save_for_backward(z_a, z_b, sums, G)
+        ctx.save_for_backward(z_a, z_b, sums, G, ws)
         ctx.meta = (B, T, D, dt, world, float(eps), group)
         return loss.to(z_a.dtype)                              # the reference's result has the input dtype
 
     @staticmethod
     def backward(ctx, grad_out):
-        z_a, z_b, sums, G = ctx.saved_tensors
+        z_a, z_b, sums, G, ws = ctx.saved_tensors
         B, T, D, dt, world, eps, group = ctx.meta
         dev = z_a.device
         st = L.stream_ptr(dev)
-        ws = L.zeroed_workspace(dev, "lfd", int(L.lib.fddm_lfd_workspace_bytes(B, T, D)))
         bn = torch.empty(4 * T * D, dtype=torch.float64, device=dev)
         dz_a = torch.empty_like(z_a)
         dz_b = torch.empty_like(z_b)
         g = grad_out.to(torch.float32).contiguous()
         args = (z_a.data_ptr(), z_b.data_ptr(), dt, B, T, D, sums.data_ptr(), float(B * world), eps, G.data_ptr(),
                 float(B * T * world), g.data_ptr(), ws.data_ptr(), bn.data_ptr())
-        L.check(L.lib.fddm_lfd_backward(*args, 0, dz_a.data_ptr(), dz_b.data_ptr(), st), "lfd_backward[0]")
+        L.check(L.lib.fddm_lfd_backward(*args, 0 | L.LFD_PLANES_VALID, dz_a.data_ptr(), dz_b.data_ptr(), st),
+                "lfd_backward[0]")
         _all_reduce(bn, group)
         L.check(L.lib.fddm_lfd_backward(*args, 1, dz_a.data_ptr(), dz_b.data_ptr(), st), "lfd_backward[1]")
         return dz_a, dz_b, None, None, None

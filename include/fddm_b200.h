@@ -152,10 +152,11 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
  *
  *   1. fddm_lfd_stats     sums = fp64 [2 tensors][2 moments][T*D]: sum_b x, sum_b x^2   (losses:23-24)
  *                         -> all-reduce sums
- *   2. fddm_lfd_xcov      cov[D,D] = sum_rows za~^T zb~ over this rank's rows, fp32.  za~ = (x-mean)/
- *                         sqrt(var+eps) with the GLOBAL-batch mean/var (n_batch_global samples) is
- *                         applied in the producer of a tcgen05 (UMMA, TMEM accumulator) contraction;
- *                         fp32 inputs are split into bf16 hi+residual (3 MMAs, ~2^-16).  losses:25-48
+ *   2. fddm_lfd_xcov      cov[D,D] = sum_rows za~^T zb~ over this rank's rows, fp32.  One pass standardises
+ *                         za~ = (x-mean)/sqrt(var+eps) with the GLOBAL-batch mean/var (n_batch_global
+ *                         samples), splits fp32 into bf16 hi+residual (3 MMAs, ~2^-16) and writes packed
+ *                         operand planes; a tcgen05 (UMMA, TMEM accumulator) contraction fed by TMA bulk
+ *                         copies does the rest; the diagonal is accumulated in fp64.       losses:25-48
  *                         -> all-reduce cov
  *   3. fddm_lfd_loss      C = cov / n_rows_global; loss = sum_j (1-C_jj)^2 + lambda sum_{j!=k} C_jk^2;
  *                         G[D,D] = dloss/dC                                               losses:51-57
@@ -168,6 +169,8 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
  * workspace: fddm_lfd_workspace_bytes(B,T,D) bytes whose first 256 bytes are zero-initialised ONCE by
  * the caller (self-resetting counters); the rest is scratch (tables, split-K partials, dz~).
  * D must be a multiple of 8 (FDDM_EUNSUPPORTED otherwise). */
+#define FDDM_LFD_PLANES_VALID 0x2  /* OR into phase 0 of fddm_lfd_backward: `workspace` still holds the
+                                      operand planes / tables written by THIS call's fddm_lfd_xcov */
 size_t fddm_lfd_workspace_bytes(int64_t B, int64_t T, int64_t D);
 int fddm_lfd_stats(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D,
                    double* sums, fddm_stream_t stream);

@@ -173,6 +173,50 @@ def test_sample_q_philox_statistics(fb):
     assert int(xt.min()) >= 0 and int(xt.max()) < K
 
 
+def test_sample_q_philox_other_ids_uniform(fb):
+    """closed-form Philox path: when the token moves, the new id is uniform over the other K-1 ids."""
+    K, T, B, L = 16, 50, 256, 256
+    s = make_sched(fb, K, T)
+    x0 = torch.full((B, L), 5, device="cuda", dtype=torch.long)
+    t = torch.full((B,), T, device="cuda", dtype=torch.long)
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    xt = s.sample_q_ids(x0, t, generator=g).flatten()
+    counts = torch.bincount(xt, minlength=K).double().cpu().numpy()
+    n = B * L
+    p = np.asarray(O.q_sample(np.eye(K, dtype=np.float32)[5][None, None], np.array([T]), s.alpha_bar.cpu().numpy()))[0, 0]
+    z = (counts - n * p) / np.sqrt(n * p * (1 - p))
+    assert np.abs(z).max() < 5.0, z
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("temp", [1.0, 0.7])
+def test_jump_philox_distribution(fb, mode, temp):
+    """in-kernel RNG (hierarchical exponential race): empirical frequencies match the target categorical."""
+    K, T_train, T_infer, r, B, L = 64, 200, 20, 5, 64, 512
+    rng = np.random.default_rng(3)
+    s = make_sched(fb, K, T_train)
+    betas, abar = s.betas.cpu().numpy(), s.alpha_bar.cpu().numpy()
+    row = (rng.normal(size=K) * 2).astype(np.float32)
+    logits = np.broadcast_to(row, (B, L, K)).copy()
+    x_t = np.full((B, L), 3, dtype=np.int64)
+    dec = ReplayDecoder([logits], torch.float32)
+    smp = fb.DiffusionJumpySampler(s, dec, K=K, T_train=T_train, T_infer=T_infer, r=r, greedy=False,
+                                   sampling_mode=mode, temperature=temp, device=torch.device("cuda"))
+    smp.generator = torch.Generator(device="cuda"); smp.generator.manual_seed(11)
+    ids, _ = smp._jump_once(dev(x_t), 20, 5, torch.zeros(B, 1, 1, device="cuda"), L)
+    _, _, p = O.jump_once(x_t[:1, :1], logits[:1, :1], 20, 5, K=K, T_train=T_train, T_infer=T_infer, betas=betas,
+                          alpha_bar=abar, sampling_mode=mode, greedy=True)
+    p = p[0, 0].astype(np.float64)
+    if temp != 1.0:
+        p = np.exp(np.log(np.maximum(p, 1e-12)) / temp)
+    p = p / p.sum()
+    n = B * L
+    counts = torch.bincount(ids.flatten(), minlength=K).double().cpu().numpy()
+    z = (counts - n * p) / np.sqrt(np.maximum(n * p * (1 - p), 1e-9))
+    assert np.abs(z[n * p > 5]).max() < 5.0, z
+    assert counts[n * p < 1e-3].sum() <= 2
+
+
 # ------------------------------------------------------------------------------------------------
 # diffusion KL (forward + gradient)
 # ------------------------------------------------------------------------------------------------

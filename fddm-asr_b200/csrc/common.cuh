@@ -129,6 +129,18 @@ __device__ __forceinline__ void stg_stream_v4(void* p, const uint4& v) {
                : "memory");
 }
 
+// MUFU approximations (2 ulp-class): exp2 and reciprocal
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ------------------------------------------------------------------------------------------------
 // dtype traits: 16-byte vectors <-> fp32
 // ------------------------------------------------------------------------------------------------

@@ -75,11 +75,20 @@ __device__ __forceinline__ void load_betas(const KlParams& p, int b, float& beta
 
 // ------------------------------------------------------------------------------------------------
 // the row math, shared by the register-resident and the shared-memory-resident paths
+//
+// Instruction budget: at 6.5 TB/s an fp32 forward+backward row stream leaves ~44 issue slots and ~5.5
+// MUFU operations per element (a bf16 forward only a quarter of that), so logs and reciprocals are
+// taken per GROUP OF 4 entries: with r_k = (p_k + eps) / (q_g + eps) (an O(1) quantity, so products of
+// four stay far inside the fp32 range),
+//   sum_k log2(q~/y_k)  = - sum_groups log2(r0 r1 r2 r3)                                  1 MUFU / 4
+//   sum_k 1/r_k         =   sum_groups ((r0+r1) r2r3 + (r2+r3) r0r1) / (r0r1r2r3)         1 MUFU / 4
+//   1/r_0               =   r1 * (r2r3) / (r0r1r2r3)   etc.  (gradient pass)              1 MUFU / 4
 // ------------------------------------------------------------------------------------------------
 template <int NT, bool BWD, typename T, class Row>
 __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt, const int x0, const float z_xt,
                                              const float z_x0, const float beta_t, const float beta_p,
                                              const float wscale, float* red, T* grad_row) {
+  constexpr float kLog2e = 1.4426950408889634f;
   const float Kf = static_cast<float>(V);
   const float a_t = 1.0f - beta_t, b_t = beta_t / Kf;
   const float a_p = 1.0f - beta_p, b_p = beta_p / Kf;
@@ -89,46 +98,66 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
   row.for_each([&](int, float& x) { m = fmaxf(m, x); });
   m = block_max<NT>(m, red);
 
-  // pass 2: e_k = exp(z_k - m) kept in place, S = sum e_k
+  // pass 2: e_k = exp(z_k - m) = 2^(z_k*log2e - m*log2e) kept in place, S = sum e_k
+  const float nm = -m * kLog2e;
   float s1[1] = {0.0f};
   row.for_each([&](int, float& x) {
-    x = __expf(x - m);
+    x = ex2_approx(fmaf(x, kLog2e, nm));
     s1[0] += x;
   });
   block_sum<NT, 1>(s1, red);
   const float inv_S = 1.0f / s1[0];
 
   const bool same = (xt == x0);
-  const float e_xt = __expf(z_xt - m), e_x0 = __expf(z_x0 - m);
+  const float e_xt = ex2_approx(fmaf(z_xt, kLog2e, nm)), e_x0 = ex2_approx(fmaf(z_x0, kLog2e, nm));
   const float xh_xt = e_xt * inv_S, xh_x0 = e_x0 * inv_S;
   const float P = (b_t + a_t * xh_xt) + kEps;
   const float Q = (b_t + (same ? a_t : 0.0f)) + kEps;
   const float inv_P = 1.0f / P;
   const float q_g = b_t * b_p / Q;
-  const float lq2 = __log2f(q_g + kEps);
-  const float c1 = b_t * a_p * inv_S * inv_P;
-  const float c0 = b_t * b_p * inv_P + kEps;
+  const float qt = q_g + kEps;                          // q~ = q_g + eps
+  const float iq = 1.0f / qt;
+  const float c1 = b_t * a_p * inv_S * inv_P;           // p_k + eps = c1*e_k + c0   (generic k)
+  const float c0e = b_t * b_p * inv_P;                  // c0 - eps
+  const float c0 = c0e + kEps;
+  const float c1r = c1 * iq, c0r = c0 * iq;             // r_k = c1r*e_k + c0r
   const float cg = q_g * b_t * a_p * inv_P;
 
-  // pass 3: generic terms for every k
+  // pass 3: generic terms for every k, four at a time
+  //   a3[0] = sum log2(q~/y_k),  a3[1] = sum 1/r_k,  a3[2] = sum e_k/r_k
   float a3[BWD ? 3 : 1];
 #pragma unroll
   for (int i = 0; i < (BWD ? 3 : 1); ++i) a3[i] = 0.0f;
-  row.for_each([&](int, float& e) {
-    const float y = fmaf(c1, e, c0);
-    a3[0] += lq2 - __log2f(y);
-    if (BWD) {
-      const float rc = __fdividef(1.0f, y);
-      a3[1] += rc;
-      a3[2] = fmaf(rc, e, a3[2]);
-    }
-  });
+  row.for_each4(
+      [&](float* e) {
+        const float r0 = fmaf(c1r, e[0], c0r), r1 = fmaf(c1r, e[1], c0r);
+        const float r2 = fmaf(c1r, e[2], c0r), r3 = fmaf(c1r, e[3], c0r);
+        const float p01 = r0 * r1, p23 = r2 * r3, pp = p01 * p23;
+        a3[0] -= __log2f(pp);
+        if (BWD) {
+          const float ip = rcp_approx(pp);
+          a3[1] = fmaf(fmaf(r0 + r1, p23, (r2 + r3) * p01), ip, a3[1]);
+          a3[2] = fmaf(fmaf(fmaf(e[0], r1, e[1] * r0), p23, fmaf(e[2], r3, e[3] * r2) * p01), ip, a3[2]);
+        }
+      },
+      [&](float& e) {
+        const float r = fmaf(c1r, e, c0r);
+        a3[0] -= __log2f(r);
+        if (BWD) {
+          const float ir = rcp_approx(r);
+          a3[1] += ir;
+          a3[2] = fmaf(e, ir, a3[2]);
+        }
+      });
   block_sum<NT, (BWD ? 3 : 1)>(a3, red);
+  // in y units: sum 1/y = iq * a3[1], sum e/y = iq * a3[2]
+  const float sum_rc = BWD ? iq * a3[1] : 0.0f, sum_erc = BWD ? iq * a3[2] : 0.0f;
 
   // exact corrections for the special entries (computed redundantly by every thread)
   float kl = q_g * (kLn2 * a3[0]);
-  float Sp = BWD ? q_g * (Kf - kEps * a3[1]) : 0.0f;
-  float G = BWD ? -cg * inv_S * a3[2] : 0.0f;
+  // S' = sum_k r_k p_k over generic entries = q_g * sum (y_k - eps)/y_k = q_g * (c1*sum e/y + (c0-eps)*sum 1/y)
+  float Sp = BWD ? q_g * fmaf(c1, sum_erc, c0e * sum_rc) : 0.0f;
+  float G = BWD ? -cg * inv_S * sum_erc : 0.0f;
   float r_sp[2], u_sp[2], xh_sp[2];
   const int n_sp = same ? 1 : 2;
 #pragma unroll
@@ -141,15 +170,15 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
       const float v = (same || !is_xt) ? (a_p + b_p) : b_p;            // train.py:230
       // what the generic formulas contributed for this k
       const float y = fmaf(c1, e, c0);
-      const float rc = __fdividef(1.0f, y);
-      kl -= q_g * (kLn2 * (lq2 - __log2f(y)));
+      const float rc = 1.0f / y;
+      kl += q_g * (kLn2 * __log2f(y * iq));
       // its true value
       const float qk = u * v / Q;
       const float pk = u * (a_p * xh + b_p) * inv_P;
       const float rk = qk / (pk + kEps);
       kl += qk * (logf(qk + kEps) - logf(pk + kEps));
       if (BWD) {
-        Sp += rk * pk - q_g * (1.0f - kEps * rc);
+        Sp += rk * pk - q_g * (y - kEps) * rc;
         G += cg * rc * xh;                                             // remove generic g_k*xh_k
         r_sp[i] = rk; u_sp[i] = u; xh_sp[i] = xh;
       }
@@ -164,14 +193,23 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
         G += g_sp[i] * xh_sp[i];
       }
     }
-    // pass 4: gradient, generic entries from registers ...
-    const float A = -wscale * inv_S * cg;
+    // pass 4: gradient  e_k * (A/y_k + Bc) = e_k * (Ar/r_k + Bc), generic entries from registers ...
+    const float Ar = -wscale * inv_S * cg * iq;
     const float Bc = -wscale * inv_S * G;
-    row.store(grad_row, [&](int, float e) {
-      const float y = fmaf(c1, e, c0);
-      const float rc = __fdividef(1.0f, y);
-      return e * fmaf(A, rc, Bc);
-    });
+    row.store4(
+        grad_row,
+        [&](const float* e, float* o) {
+          const float r0 = fmaf(c1r, e[0], c0r), r1 = fmaf(c1r, e[1], c0r);
+          const float r2 = fmaf(c1r, e[2], c0r), r3 = fmaf(c1r, e[3], c0r);
+          const float p01 = r0 * r1, p23 = r2 * r3;
+          const float ip = rcp_approx(p01 * p23);
+          const float h01 = p23 * ip, h23 = p01 * ip;                  // 1/(r0 r1), 1/(r2 r3)
+          o[0] = e[0] * fmaf(Ar, r1 * h01, Bc);
+          o[1] = e[1] * fmaf(Ar, r0 * h01, Bc);
+          o[2] = e[2] * fmaf(Ar, r3 * h23, Bc);
+          o[3] = e[3] * fmaf(Ar, r2 * h23, Bc);
+        },
+        [&](float e) { return e * fmaf(Ar, rcp_approx(fmaf(c1r, e, c0r)), Bc); });
     // ... then the special entries overwritten with their exact values
     consumer_sync<NT>();
     if (threadIdx.x == 0) {

@@ -450,7 +450,7 @@ int launch_finalize(const void* za, const void* zb, int dtype, int64_t B, int64_
 // number of split-K slices for the forward contraction: fill the SMs, >= 2 k-blocks per slice
 int pick_splits(int64_t tiles, int64_t rows) {
   const int sms = num_sms();
-  int64_t s = std::max<int64_t>(1, (sms + tiles - 1) / tiles);
+  int64_t s = std::max<int64_t>(1, sms / tiles);             // tiles*splits <= SM count: exactly one wave
   s = std::min<int64_t>(s, std::max<int64_t>(1, rows / 64));
   s = std::min<int64_t>(s, LfdWorkspace::kMaxSplits);
   return static_cast<int>(s);

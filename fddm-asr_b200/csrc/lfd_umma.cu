@@ -18,6 +18,10 @@
 // tile), i.e. 8-row x 16-byte core matrices of 128 contiguous bytes.
 //   MN index = column (forward):  R = BK rows;  MN-major descriptor, SBO = BK*16, LBO = 128
 //   MN index = row    (backward): R = TM rows;  K-major descriptor,  SBO = 128,   LBO = TM*16
+#include <cuda.h>      // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through the runtime)
+
+#include <string.h>
+
 #include <algorithm>
 
 #include "lfd_common.cuh"
@@ -89,6 +93,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 2-D tiled TMA load (SASS UTMALDG) completing on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // number of bulk copies / bytes per copy that fill one plane of an operand tile
 struct TilePlan {
   int ncopies;
@@ -112,8 +125,14 @@ __device__ __forceinline__ TilePlan plan_tile(const PackedOperand& op, int64_t m
   return t;
 }
 
+// The four tensor maps describe the (hi, lo) planes of A and B as 2-D arrays [C_pad/8][R_pad*8]: an
+// MN-major tile (BK rows x TM/8 chunk columns) is then ONE box {BK*8 elements, TM/8} that lands densely
+// in the canonical layout.  They are only dereferenced for operands with mn_is_col == 1; K-major tiles
+// are a few long contiguous runs and use 1-D bulk copies.
 template <int TERMS>
-__global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_accum;
   __shared__ uint32_t s_tmem_base;
@@ -131,6 +150,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
   const int num_kb = static_cast<int>((k_end - k_begin + kBK - 1) / kBK);   // padded planes hold zeros past K
 
   if (tid == 0) {
+    if (p.A.mn_is_col) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+      if (TERMS == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    }
+    if (p.B.mn_is_col) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+      if (TERMS == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 1);
@@ -168,10 +195,18 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
         const __nv_bfloat16* pb = term == 0 ? p.B.hi : p.B.lo;
         uint8_t* da = st + term * kTileA;
         uint8_t* db = st + TERMS * kTileA + term * kTileB;
-        for (int c = lane; c < ta.ncopies; c += 32)
-          tma_load_1d(da + static_cast<size_t>(c) * ta.bytes, pa + ta.src_base + c * ta.src_stride, ta.bytes, &s_full[s]);
-        for (int c = lane; c < tb.ncopies; c += 32)
-          tma_load_1d(db + static_cast<size_t>(c) * tb.bytes, pb + tb.src_base + c * tb.src_stride, tb.bytes, &s_full[s]);
+        if (p.A.mn_is_col) {
+          if (lane == 0) tma_load_2d(da, term == 0 ? &tmA_hi : &tmA_lo, static_cast<int>(k0 * 8), static_cast<int>(m0 / 8), &s_full[s]);
+        } else {
+          for (int c = lane; c < ta.ncopies; c += 32)
+            tma_load_1d(da + static_cast<size_t>(c) * ta.bytes, pa + ta.src_base + c * ta.src_stride, ta.bytes, &s_full[s]);
+        }
+        if (p.B.mn_is_col) {
+          if (lane == 1) tma_load_2d(db, term == 0 ? &tmB_hi : &tmB_lo, static_cast<int>(k0 * 8), static_cast<int>(n0 / 8), &s_full[s]);
+        } else {
+          for (int c = lane; c < tb.ncopies; c += 32)
+            tma_load_1d(db + static_cast<size_t>(c) * tb.bytes, pb + tb.src_base + c * tb.src_stride, tb.bytes, &s_full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -242,6 +277,43 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const GemmParams
   }
 }
 
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// plane [C_pad/8][R_pad*8] bf16, box {BK*8, mn_extent/8}, no swizzle, no interleave
+int make_plane_map(CUtensorMap* tm, const __nv_bfloat16* plane, int64_t R_pad, int64_t C_pad, int mn_extent) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) {
+    set_error("umma_gemm: cuTensorMapEncodeTiled is not available from the driver");
+    return FDDM_ECUDA;
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(R_pad) * 8, static_cast<cuuint64_t>(C_pad / 8)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(R_pad) * 16};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK * 8), static_cast<cuuint32_t>(mn_extent / 8)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(plane), gdim, gstride, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("umma_gemm: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return FDDM_ECUDA;
+  }
+  return FDDM_OK;
+}
+
 bool operand_ok(const PackedOperand& o, int terms) {
   return o.hi && (terms == 1 || o.lo) && reinterpret_cast<uintptr_t>(o.hi) % 16 == 0 &&
          reinterpret_cast<uintptr_t>(o.lo) % 16 == 0 && o.R_pad % kPackPad == 0 && o.C_pad % kPackPad == 0;
@@ -286,14 +358,24 @@ int umma_gemm(const PackedOperand& A, const PackedOperand& B, int64_t M, int64_t
   if (p.splits < splits && out_split_stride > 0)
     FDDM_CUDA_OK(cudaMemsetAsync(out + static_cast<int64_t>(p.splits) * out_split_stride, 0,
                                  sizeof(float) * static_cast<size_t>(splits - p.splits) * out_split_stride, stream));
+  CUtensorMap tm[4];
+  memset(tm, 0, sizeof(tm));
+  if (A.mn_is_col) {
+    if (int rc = make_plane_map(&tm[0], A.hi, A.R_pad, A.C_pad, kBM)) return rc;
+    if (terms == 2) if (int rc = make_plane_map(&tm[1], A.lo, A.R_pad, A.C_pad, kBM)) return rc;
+  }
+  if (B.mn_is_col) {
+    if (int rc = make_plane_map(&tm[2], B.hi, B.R_pad, B.C_pad, p.BN)) return rc;
+    if (terms == 2) if (int rc = make_plane_map(&tm[3], B.lo, B.R_pad, B.C_pad, p.BN)) return rc;
+  }
   if (terms == 2) {
     FDDM_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    umma_gemm_kernel<2><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+    umma_gemm_kernel<2><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p, tm[0], tm[1], tm[2], tm[3]);
   } else {
     FDDM_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    umma_gemm_kernel<1><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+    umma_gemm_kernel<1><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p, tm[0], tm[1], tm[2], tm[3]);
   }
   FDDM_LAUNCH_OK();
   return FDDM_OK;

@@ -56,6 +56,32 @@ struct RegRow {
       }
     }
   }
+  // f4(x4) over groups of 4 consecutive valid elements (x4 points at 4 registers)
+  template <class F4, class F1>
+  __device__ __forceinline__ void for_each4(F4&& f4, F1&&) {
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int vi = j * NT + tid;
+      if (vi < nvec) {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) f4(&v[j * N + 4 * q]);
+      }
+    }
+  }
+  // dst[k..k+3] = g4(x4, o4) for the whole row, 128-bit streaming stores
+  template <class G4, class G1>
+  __device__ __forceinline__ void store4(T* dst, G4&& g4, G1&&) {
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int vi = j * NT + tid;
+      if (vi < nvec) {
+        float o[N];
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) g4(&v[j * N + 4 * q], &o[4 * q]);
+        stg_stream_v4(reinterpret_cast<uint4*>(dst) + vi, Vec16<T>::pack(o));
+      }
+    }
+  }
   // dst[k] = g(k, x) for the whole row, 128-bit streaming stores
   template <class G>
   __device__ __forceinline__ void store(T* dst, G&& g) {
@@ -92,6 +118,24 @@ struct SmemRow {
   template <class G>
   __device__ __forceinline__ void store(T* dst, G&& g) {
     for (int k = tid; k < V; k += NT) Vec16<T>::store1(dst + k, g(k, r[k]));
+  }
+  // groups of 4 consecutive elements, then the (V % 4) tail one by one
+  template <class F4, class F1>
+  __device__ __forceinline__ void for_each4(F4&& f4, F1&& f1) {
+    const int V4 = V & ~3;
+    for (int k = 4 * tid; k < V4; k += 4 * NT) f4(&r[k]);
+    for (int k = V4 + tid; k < V; k += NT) f1(r[k]);
+  }
+  template <class G4, class G1>
+  __device__ __forceinline__ void store4(T* dst, G4&& g4, G1&& g1) {
+    const int V4 = V & ~3;
+    for (int k = 4 * tid; k < V4; k += 4 * NT) {
+      float o[4];
+      g4(&r[k], o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Vec16<T>::store1(dst + k + e, o[e]);
+    }
+    for (int k = V4 + tid; k < V; k += NT) Vec16<T>::store1(dst + k, g1(r[k]));
   }
 };
 

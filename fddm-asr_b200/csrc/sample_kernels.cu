@@ -237,24 +237,32 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
   const bool sample = (p.flags & FDDM_JUMP_SAMPLE) != 0;
   const bool write_p = (p.flags & FDDM_JUMP_WRITE_P) != 0;
 
-  // softmax in the logits dtype (F.softmax, sampler:189): exp(z-m)/S, rounded to T
+  // softmax in the logits dtype (F.softmax, sampler:189): exp(z-m)/S, rounded to T.
+  // FAST (in-kernel RNG: the drawn ids cannot be compared with the reference's anyway) uses MUFU
+  // ex2 and a multiply by 1/S; otherwise libm expf and an IEEE division so that the probabilities
+  // that decide argmax / the injected-noise race are the reference's bit for bit wherever possible.
+  constexpr bool FAST = std::is_same<NoiseT, NoisePhilox>::value;
+  constexpr float kLog2e = 1.4426950408889634f;
   float m = kNegInf;
   row.for_each([&](int, float& x) { m = fmaxf(m, x); });
   m = block_max<NT>(m, red);
+  const float nm = -m * kLog2e;
   float s1[1] = {0.0f};
   row.for_each([&](int, float& x) {
-    x = expf(x - m);
+    x = FAST ? ex2_approx(fmaf(x, kLog2e, nm)) : expf(x - m);
     s1[0] += x;
   });
   block_sum<NT, 1>(s1, red);
   const float S = s1[0];
+  const float inv_S = 1.0f / S;
   float s2[1] = {0.0f};
   float pm = -1.0f;
   int pm_k = 0x7fffffff;
+  const bool want_amax = (argmax_p != nullptr);
   row.for_each([&](int k, float& x) {
-    x = Vec16<T>::round_trip(__fdiv_rn(x, S));
+    x = Vec16<T>::round_trip(FAST ? x * inv_S : __fdiv_rn(x, S));
     s2[0] += x;
-    if (x > pm) { pm = x; pm_k = k; }
+    if (want_amax && x > pm) { pm = x; pm_k = k; }
   });
   if (write_p) row.store(p_row_out, [](int, float x) { return x; });
   if (argmax_p != nullptr) {
@@ -279,9 +287,10 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
   }
   auto value = [&](int k, float xh) -> float {
     if (exact) {
-      const float Bk = __fadd_rn(__fmul_rn(c.a_g, xh), bs);
+      const float Bk = FAST ? fmaf(c.a_g, xh, bs) : __fadd_rn(__fmul_rn(c.a_g, xh), bs);
       return __fmul_rn(k == c.xt ? A_xt : A_gen, Bk);
     }
+    if (FAST && sizeof(T) == 4) return fmaf(ab, xh, mixu);
     return Vec16<T>::round_trip(__fadd_rn(Vec16<T>::round_trip(__fmul_rn(ab, xh)), mixu));
   };
 

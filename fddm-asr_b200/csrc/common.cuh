@@ -98,6 +98,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// producer-side wait: a single lane spinning at full rate steals issue slots from the consumers
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -210,12 +214,27 @@ struct Vec16<__half> {
 };
 
 // ------------------------------------------------------------------------------------------------
-// block reductions (warp shuffle, then one shared-memory hop across warps).  `red` is a shared
-// scratch of >= 4*32 floats; every thread gets the result.  Deterministic (fixed tree).
+// block reductions: warp shuffle, one shared-memory hop across warps, ONE named barrier each.
+// The scratch is a ring of three regions used round-robin (all threads call in lockstep): a region is
+// rewritten only two reductions -- hence two barriers -- after it was read, so no trailing barrier
+// is needed to protect it.  Every thread gets the result.  Deterministic (fixed tree).
 // ------------------------------------------------------------------------------------------------
+constexpr int kRedRegion = 128;                 // floats per region: up to 4 values x 32 warps
+constexpr int kRedFloats = 3 * kRedRegion;
+struct RedRing {
+  float* base;
+  int idx;
+  __device__ __forceinline__ float* next() {
+    float* r = base + idx * kRedRegion;
+    idx = (idx == 2) ? 0 : idx + 1;
+    return r;
+  }
+};
+
 template <int NT>
-__device__ __forceinline__ float block_max(float v, float* red) {
+__device__ __forceinline__ float block_max(float v, RedRing& rr) {
   constexpr int NW = NT / 32;
+  float* red = rr.next();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
@@ -223,13 +242,14 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   float r = red[0];
 #pragma unroll
   for (int w = 1; w < NW; ++w) r = fmaxf(r, red[w]);
-  consumer_sync<NT>();
   return r;
 }
 
 template <int NT, int NV>
-__device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
+__device__ __forceinline__ void block_sum(float (&v)[NV], RedRing& rr) {
   constexpr int NW = NT / 32;
+  static_assert(NV <= 4, "region holds 4 values per warp");
+  float* red = rr.next();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
 #pragma unroll
@@ -247,7 +267,32 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
     for (int w = 1; w < NW; ++w) r += red[i * 32 + w];
     v[i] = r;
   }
+}
+
+// Softmax statistics in one reduction: in (m, s) = this thread's max and sum_k exp(x_k - m);
+// out (m, s) = the row max and sum_k exp(x_k - row max).  Pairs combine as
+// (m1,s1) + (m2,s2) = (max, s1*2^((m1-max)*log2e) + s2*2^((m2-max)*log2e)).
+template <int NT>
+__device__ __forceinline__ void block_softmax_stats(float& m, float& s, RedRing& rr) {
+  constexpr int NW = NT / 32;
+  constexpr float kLog2e = 1.4426950408889634f;
+  float* red = rr.next();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = s * ex2_approx((m - nm) * kLog2e) + os * ex2_approx((om - nm) * kLog2e);
+    m = nm;
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; red[32 + (threadIdx.x >> 5)] = s; }
   consumer_sync<NT>();
+  float gm = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) gm = fmaxf(gm, red[w]);
+  float gs = 0.0f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) gs = fmaf(red[32 + w], ex2_approx((red[w] - gm) * kLog2e), gs);
+  m = gm; s = gs;
 }
 
 // argmax with torch semantics: larger value wins, equal values -> lower index.
@@ -256,8 +301,9 @@ __device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int o
 }
 
 template <int NT>
-__device__ __forceinline__ void block_argmax(float& v, int& idx, float* red) {
+__device__ __forceinline__ void block_argmax(float& v, int& idx, RedRing& rr) {
   constexpr int NW = NT / 32;
+  float* red = rr.next();
   int* redi = reinterpret_cast<int*>(red) + 32;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -271,7 +317,15 @@ __device__ __forceinline__ void block_argmax(float& v, int& idx, float* red) {
 #pragma unroll
   for (int w = 1; w < NW; ++w) argmax_combine(r, ri, red[w], redi[w]);
   v = r; idx = ri;
+}
+
+// one value from one thread to all (1 barrier)
+template <int NT>
+__device__ __forceinline__ int block_broadcast_int(bool is_source, int value, RedRing& rr) {
+  int* red = reinterpret_cast<int*>(rr.next());
+  if (is_source) red[0] = value;
   consumer_sync<NT>();
+  return red[0];
 }
 
 // ------------------------------------------------------------------------------------------------

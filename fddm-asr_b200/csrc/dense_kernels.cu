@@ -58,7 +58,8 @@ template <bool REG>
 __global__ void __launch_bounds__(kNT) q_sample_dense_kernel(const float* __restrict__ x0, const int64_t* __restrict__ t,
                                                              const float* __restrict__ alpha_bar, int T, int L, int K,
                                                              int rows, float eps, float u, float* __restrict__ out) {
-  __shared__ float red[4 * 32];
+  __shared__ float s_red[kRedFloats];
+  RedRing red{s_red, 0};
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const float ab = alpha_bar[clamp_t(t[row / L], T) - 1];
     const float om = __fmul_rn(__fsub_rn(1.0f, ab), u);                       // (1-abar)*u      sched:47
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(kNT) q_posterior_dense_kernel(const float* __r
                                                                 const float* __restrict__ betas,
                                                                 const float* __restrict__ coeffs, int T, int B, int L,
                                                                 int K, int rows, float eps, float* __restrict__ out) {
-  __shared__ float red[4 * 32];
+  __shared__ float s_red[kRedFloats];
+  RedRing red{s_red, 0};
   const float Kf = static_cast<float>(K);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int b = row / L;

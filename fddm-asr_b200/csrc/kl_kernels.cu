@@ -87,40 +87,45 @@ __device__ __forceinline__ void load_betas(const KlParams& p, int b, float& beta
 template <int NT, bool BWD, typename T, class Row>
 __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt, const int x0, const float z_xt,
                                              const float z_x0, const float beta_t, const float beta_p,
-                                             const float wscale, float* red, T* grad_row) {
+                                             const float wscale, RedRing& red, T* grad_row) {
   constexpr float kLog2e = 1.4426950408889634f;
   const float Kf = static_cast<float>(V);
   const float a_t = 1.0f - beta_t, b_t = beta_t / Kf;
   const float a_p = 1.0f - beta_p, b_p = beta_p / Kf;
 
-  // pass 1: row max
-  float m = kNegInf;
-  row.for_each([&](int, float& x) { m = fmaxf(m, x); });
-  m = block_max<NT>(m, red);
-
-  // pass 2: e_k = exp(z_k - m) = 2^(z_k*log2e - m*log2e) kept in place, S = sum e_k
-  const float nm = -m * kLog2e;
-  float s1[1] = {0.0f};
+  // passes 1+2: per-thread max m_t and e_k = exp(z_k - m_t) kept in place, then ONE block reduction of the
+  // (max, sum) pairs gives the row max m and S = sum_k exp(z_k - m).  The registers keep exp(z_k - m_t);
+  // the per-thread factor f_t = exp(m_t - m) is folded into the coefficients of the later passes.
+  float m_t = kNegInf;
+  row.for_each([&](int, float& x) { m_t = fmaxf(m_t, x); });
+  const float nm_t = -m_t * kLog2e;
+  float s_t = 0.0f;
   row.for_each([&](int, float& x) {
-    x = ex2_approx(fmaf(x, kLog2e, nm));
-    s1[0] += x;
+    x = ex2_approx(fmaf(x, kLog2e, nm_t));
+    s_t += x;
   });
-  block_sum<NT, 1>(s1, red);
-  const float inv_S = 1.0f / s1[0];
+  float m = m_t, S = s_t;
+  block_softmax_stats<NT>(m, S, red);
+  const float f_t = ex2_approx((m_t - m) * kLog2e);
+  const float nm = -m * kLog2e;
+  // Row scalars are evaluated redundantly by every thread, so they use MUFU reciprocals / logs
+  // (~1e-7 relative, far inside the 1e-5 bar) instead of IEEE division / libm sequences.
+  const float inv_S = rcp_approx(S);
 
   const bool same = (xt == x0);
   const float e_xt = ex2_approx(fmaf(z_xt, kLog2e, nm)), e_x0 = ex2_approx(fmaf(z_x0, kLog2e, nm));
   const float xh_xt = e_xt * inv_S, xh_x0 = e_x0 * inv_S;
   const float P = (b_t + a_t * xh_xt) + kEps;
   const float Q = (b_t + (same ? a_t : 0.0f)) + kEps;
-  const float inv_P = 1.0f / P;
-  const float q_g = b_t * b_p / Q;
+  const float inv_P = rcp_approx(P), inv_Q = rcp_approx(Q);
+  const float q_g = b_t * b_p * inv_Q;
   const float qt = q_g + kEps;                          // q~ = q_g + eps
-  const float iq = 1.0f / qt;
+  const float iq = rcp_approx(qt);
   const float c1 = b_t * a_p * inv_S * inv_P;           // p_k + eps = c1*e_k + c0   (generic k)
   const float c0e = b_t * b_p * inv_P;                  // c0 - eps
   const float c0 = c0e + kEps;
-  const float c1r = c1 * iq, c0r = c0 * iq;             // r_k = c1r*e_k + c0r
+  const float c0r = c0 * iq;
+  const float c1r = c1 * iq * f_t;                      // r_k = c1r*e_k + c0r with e_k relative to m_t
   const float cg = q_g * b_t * a_p * inv_P;
 
   // pass 3: generic terms for every k, four at a time
@@ -149,6 +154,7 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
           a3[2] = fmaf(e, ir, a3[2]);
         }
       });
+  if (BWD) a3[2] *= f_t;                                // sum e_k/r_k in units of exp(z_k - m)
   block_sum<NT, (BWD ? 3 : 1)>(a3, red);
   // in y units: sum 1/y = iq * a3[1], sum e/y = iq * a3[2]
   const float sum_rc = BWD ? iq * a3[1] : 0.0f, sum_erc = BWD ? iq * a3[2] : 0.0f;
@@ -170,13 +176,13 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
       const float v = (same || !is_xt) ? (a_p + b_p) : b_p;            // train.py:230
       // what the generic formulas contributed for this k
       const float y = fmaf(c1, e, c0);
-      const float rc = 1.0f / y;
+      const float rc = rcp_approx(y);
       kl += q_g * (kLn2 * __log2f(y * iq));
       // its true value
-      const float qk = u * v / Q;
+      const float qk = u * v * inv_Q;
       const float pk = u * (a_p * xh + b_p) * inv_P;
-      const float rk = qk / (pk + kEps);
-      kl += qk * (logf(qk + kEps) - logf(pk + kEps));
+      const float rk = qk * rcp_approx(pk + kEps);
+      kl += qk * (kLn2 * (__log2f(qk + kEps) - __log2f(pk + kEps)));
       if (BWD) {
         Sp += rk * pk - q_g * (y - kEps) * rc;
         G += cg * rc * xh;                                             // remove generic g_k*xh_k
@@ -194,8 +200,8 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
       }
     }
     // pass 4: gradient  e_k * (A/y_k + Bc) = e_k * (Ar/r_k + Bc), generic entries from registers ...
-    const float Ar = -wscale * inv_S * cg * iq;
-    const float Bc = -wscale * inv_S * G;
+    const float Ar = -wscale * inv_S * cg * iq * f_t;   // e_k here is exp(z_k - m_t): fold f_t in
+    const float Bc = -wscale * inv_S * G * f_t;
     row.store4(
         grad_row,
         [&](const float* e, float* o) {
@@ -281,7 +287,7 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages];
   __shared__ RingMeta s_meta[kMaxStages];
-  __shared__ float s_red[4 * 32];
+  __shared__ float s_red[kRedFloats];
   __shared__ int s_flag;
 
   Ring ring;
@@ -302,7 +308,7 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
     int s = 0;
     uint32_t round = 0;
     for (;;) {
-      if (round > 0) mbar_wait(&ring.empty[s], (round - 1) & 1);
+      if (round > 0) mbar_wait_backoff(&ring.empty[s], (round - 1) & 1);
       int row = 0;
       if (lane == 0) row = static_cast<int>(atomicAdd(&p.ws->next_row, 1u));
       row = __shfl_sync(0xffffffffu, row, 0);
@@ -338,6 +344,7 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
 
   // ===== consumers =====
   const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
+  RedRing red{s_red, 0};
   RegRow<T, NT, EPT> row;
   row.tid = tid;
   row.nvec = p.V / RegRow<T, NT, EPT>::N;
@@ -358,7 +365,7 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
       const float z_xt = Vec16<T>::load1(st + mt.i0);
       const float z_x0 = Vec16<T>::load1(st + mt.i1);
       ring_release(ring, s);
-      const float kl = kl_row_math<NT, BWD, T>(row, p.V, mt.i0, mt.i1, z_xt, z_x0, mt.f0, mt.f1, mt.w * gscale, s_red,
+      const float kl = kl_row_math<NT, BWD, T>(row, p.V, mt.i0, mt.i1, z_xt, z_x0, mt.f0, mt.f1, mt.w * gscale, red,
                                                grad_row);
       if (tid == 0) p.ws->kl_tok[mt.row] = kl;
     }
@@ -373,11 +380,12 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
 template <typename T, int NT, bool BWD>
 __global__ void __launch_bounds__(NT, 1) kl_rows_generic_kernel(const KlParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
-  __shared__ float s_red[4 * 32];
+  __shared__ float s_red[kRedFloats];
   __shared__ int s_flag;
   float* srow = reinterpret_cast<float*>(dyn_smem);
   const int tid = threadIdx.x;
   const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
+  RedRing red{s_red, 0};
   SmemRow<T, NT> row;
   for (int r = blockIdx.x; r < p.rows; r += gridDim.x) {
     const float w = token_weight_warp(p, r, tid & 31);
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) kl_rows_generic_kernel(const KlParams p
     float beta_t, beta_p;
     load_betas(p, r / p.L, beta_t, beta_p);
     consumer_sync<NT>();      // everyone has read the specials before pass 2 overwrites the row
-    const float kl = kl_row_math<NT, BWD, T>(row, p.V, xt, x0, z_xt, z_x0, beta_t, beta_p, w * gscale, s_red, grad_row);
+    const float kl = kl_row_math<NT, BWD, T>(row, p.V, xt, x0, z_xt, z_x0, beta_t, beta_p, w * gscale, red, grad_row);
     if (tid == 0) p.ws->kl_tok[r] = kl;
     consumer_sync<NT>();      // row buffer is reused by the next iteration
   }

@@ -56,6 +56,19 @@ struct RegRow {
       }
     }
   }
+  // Unpredicated variants: visit ALL registers, including the padding lanes past the end of the row
+  // (they hold kNegInf after load_from_smem, i.e. exp() == 0).  Callers correct their sums by n_pad().
+  __device__ __forceinline__ int n_pad() const { return NT * EPT - nvec * N; }
+  template <class F>
+  __device__ __forceinline__ void for_all(F&& f) {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) f(v[i]);
+  }
+  template <class F4, class F1>
+  __device__ __forceinline__ void for_all4(F4&& f4, F1&&) {
+#pragma unroll
+    for (int i = 0; i < EPT; i += 4) f4(&v[i]);
+  }
   // f4(x4) over groups of 4 consecutive valid elements (x4 points at 4 registers)
   template <class F4, class F1>
   __device__ __forceinline__ void for_each4(F4&& f4, F1&&) {
@@ -111,14 +124,34 @@ struct SmemRow {
     for (int k = tid; k < V; k += NT) r[k] = Vec16<T>::load1(src + k);
     consumer_sync<NT>();
   }
+  // Element ownership is the same in every visitor (kernels keep per-thread state such as a local
+  // softmax max between passes): thread t owns the 4-element groups t, t+NT, ... and, of the V % 4
+  // tail, element V4 + t.
   template <class F>
   __device__ __forceinline__ void for_each(F&& f) {
-    for (int k = tid; k < V; k += NT) f(k, r[k]);
+    const int V4 = V & ~3;
+    for (int k = 4 * tid; k < V4; k += 4 * NT) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f(k + e, r[k + e]);
+    }
+    for (int k = V4 + tid; k < V; k += NT) f(k, r[k]);
   }
   template <class G>
   __device__ __forceinline__ void store(T* dst, G&& g) {
-    for (int k = tid; k < V; k += NT) Vec16<T>::store1(dst + k, g(k, r[k]));
+    const int V4 = V & ~3;
+    for (int k = 4 * tid; k < V4; k += 4 * NT) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Vec16<T>::store1(dst + k + e, g(k + e, r[k + e]));
+    }
+    for (int k = V4 + tid; k < V; k += NT) Vec16<T>::store1(dst + k, g(k, r[k]));
   }
+  __device__ __forceinline__ int n_pad() const { return 0; }
+  template <class F>
+  __device__ __forceinline__ void for_all(F&& f) {
+    for (int k = tid; k < V; k += NT) f(r[k]);
+  }
+  template <class F4, class F1>
+  __device__ __forceinline__ void for_all4(F4&& f4, F1&& f1) { for_each4(f4, f1); }
   // groups of 4 consecutive elements, then the (V % 4) tail one by one
   template <class F4, class F1>
   __device__ __forceinline__ void for_each4(F4&& f4, F1&& f1) {

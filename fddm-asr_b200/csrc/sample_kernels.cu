@@ -73,7 +73,7 @@ __device__ __forceinline__ void for_each_noise(RegRow<T, NT, EPT>& row, const No
 }
 template <typename T, int NT, class Noise, class F>
 __device__ __forceinline__ void for_each_noise(SmemRow<T, NT>& row, const Noise& nz, F&& f) {
-  for (int k = row.tid; k < row.V; k += NT) f(k, row.r[k], nz.load1(k));
+  row.for_each([&](int k, float& x) { f(k, x, nz.load1(k)); });
 }
 
 #ifndef FDDM_JUMP_DT
@@ -104,7 +104,8 @@ __device__ __forceinline__ void q_sample_two_values(float ab, float u, float eps
 
 template <int NT, bool PHILOX>
 __global__ void __launch_bounds__(NT) sample_q_kernel(const SampleQParams p) {
-  __shared__ float s_red[4 * 32];
+  __shared__ float s_red[kRedFloats];
+  RedRing red{s_red, 0};
   const int tid = threadIdx.x;
   const bool vec = (p.K % 4 == 0) && (PHILOX || reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
   for (int row = blockIdx.x; row < p.rows; row += gridDim.x) {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(NT) sample_q_kernel(const SampleQParams p) {
     } else {
       for (int k = tid; k < p.K; k += NT) visit(k, PHILOX ? ph.load1(k) : nrow[k]);
     }
-    block_argmax<NT>(best, best_k, s_red);
+    block_argmax<NT>(best, best_k, red);
     if (tid == 0) p.out[row] = best_k;
   }
 }
@@ -232,7 +233,7 @@ struct JumpRowCtx {
 // One row: returns the new id (valid in every thread).  `NoiseT` provides E_k when sampling.
 template <int NT, typename T, class Row, class NoiseT>
 __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, const JumpRowCtx& c, const NoiseT& nz,
-                                             float* red, T* p_row_out, int* argmax_p) {
+                                             RedRing& red, T* p_row_out, int* argmax_p) {
   const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
   const bool sample = (p.flags & FDDM_JUMP_SAMPLE) != 0;
   const bool write_p = (p.flags & FDDM_JUMP_WRITE_P) != 0;
@@ -243,27 +244,50 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
   // that decide argmax / the injected-noise race are the reference's bit for bit wherever possible.
   constexpr bool FAST = std::is_same<NoiseT, NoisePhilox>::value;
   constexpr float kLog2e = 1.4426950408889634f;
-  float m = kNegInf;
-  row.for_each([&](int, float& x) { m = fmaxf(m, x); });
-  m = block_max<NT>(m, red);
-  const float nm = -m * kLog2e;
-  float s1[1] = {0.0f};
-  row.for_each([&](int, float& x) {
-    x = FAST ? ex2_approx(fmaf(x, kLog2e, nm)) : expf(x - m);
-    s1[0] += x;
-  });
-  block_sum<NT, 1>(s1, red);
-  const float S = s1[0];
-  const float inv_S = 1.0f / S;
+  float S, inv_S;
   float s2[1] = {0.0f};
   float pm = -1.0f;
   int pm_k = 0x7fffffff;
   const bool want_amax = (argmax_p != nullptr);
-  row.for_each([&](int k, float& x) {
-    x = Vec16<T>::round_trip(FAST ? x * inv_S : __fdiv_rn(x, S));
-    s2[0] += x;
-    if (want_amax && x > pm) { pm = x; pm_k = k; }
-  });
+  if (FAST) {
+    // per-thread max and exp-sum, ONE block reduction of the (max, sum) pairs, then
+    // p_k = exp(z_k - m_t) * (exp(m_t - m) / S)
+    float m_t = kNegInf;
+    row.for_each([&](int, float& x) { m_t = fmaxf(m_t, x); });
+    const float nm_t = -m_t * kLog2e;
+    float s_t = 0.0f;
+    row.for_each([&](int, float& x) {
+      x = ex2_approx(fmaf(x, kLog2e, nm_t));
+      s_t += x;
+    });
+    float m = m_t;
+    S = s_t;
+    block_softmax_stats<NT>(m, S, red);
+    inv_S = rcp_approx(S);
+    const float sc = ex2_approx((m_t - m) * kLog2e) * inv_S;
+    row.for_each([&](int k, float& x) {
+      x = Vec16<T>::round_trip(x * sc);
+      if (want_amax && x > pm) { pm = x; pm_k = k; }
+    });
+    s2[0] = S * inv_S;                               // sum of p (== 1 up to rounding): no reduction needed
+  } else {
+    float m = kNegInf;
+    row.for_each([&](int, float& x) { m = fmaxf(m, x); });
+    m = block_max<NT>(m, red);
+    float s1[1] = {0.0f};
+    row.for_each([&](int, float& x) {
+      x = expf(x - m);
+      s1[0] += x;
+    });
+    block_sum<NT, 1>(s1, red);
+    S = s1[0];
+    inv_S = 1.0f / S;
+    row.for_each([&](int k, float& x) {
+      x = Vec16<T>::round_trip(__fdiv_rn(x, S));
+      s2[0] += x;
+      if (want_amax && x > pm) { pm = x; pm_k = k; }
+    });
+  }
   if (write_p) row.store(p_row_out, [](int, float x) { return x; });
   if (argmax_p != nullptr) {
     block_argmax<NT>(pm, pm_k, red);
@@ -275,7 +299,7 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
   float bs = 0.0f, A_gen = 0.0f, A_xt = 0.0f, ab = 0.0f, mixu = 0.0f;
   float sum_xh = 0.0f;
   if (exact) {
-    block_sum<NT, 1>(s2, red);
+    if (!FAST) block_sum<NT, 1>(s2, red);
     sum_xh = s2[0];
     bs = __fmul_rn(c.b_g, sum_xh);                                 // b_tgt * sum(x0hat)     sched:191
     A_gen = c.b_c;                                                 // a*0 + b*sum_xt*1       sched:187
@@ -341,7 +365,7 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
       best = __fdividef(mass, exp1_from_bits(rnd.x));
       best_k = row.tid;
       block_argmax<NT>(best, best_k, red);
-      int* pick = reinterpret_cast<int*>(red) + 64;
+      int picked = 0;
       if (row.tid == best_k) {
         const float target = mass * ((static_cast<float>(rnd.y >> 8) + 1.0f) * (1.0f / 16777216.0f));
         float cum = 0.0f;
@@ -354,12 +378,9 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
             if (cum >= target) chosen = k;
           }
         });
-        *pick = (chosen < 0) ? last_pos : chosen;
+        picked = (chosen < 0) ? last_pos : chosen;
       }
-      consumer_sync<NT>();
-      const int res = *pick;
-      consumer_sync<NT>();
-      return res;
+      return block_broadcast_int<NT>(row.tid == best_k, picked, red);
     } else {
       // injected noise: the reference's per-entry race argmax_k w_k / E_k, bit for bit
       for_each_noise(row, nz, [&](int k, float& xh, float E) {
@@ -410,7 +431,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages];
   __shared__ RingMeta s_meta[kMaxStages];
-  __shared__ float s_red[4 * 32];
+  __shared__ float s_red[kRedFloats];
 
   Ring ring;
   ring.stages = dyn_smem;
@@ -430,7 +451,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
       int s = 0;
       uint32_t round = 0;
       for (;;) {
-        if (round > 0) mbar_wait(&ring.empty[s], (round - 1) & 1);
+        if (round > 0) mbar_wait_backoff(&ring.empty[s], (round - 1) & 1);
         const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
         if (row >= p.rows) {
           ring.meta[s].row = -1;
@@ -455,6 +476,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     return;
   }
 
+  RedRing red{s_red, 0};
   RegRow<T, NT, EPT> row;
   int s = 0;
   uint32_t round = 0;
@@ -473,12 +495,12 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     if (NOISE == 2) {
       NoisePhilox nz;
       nz.key = p.key; nz.row = static_cast<uint32_t>(mt.row); nz.off = p.off;
-      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
       nz.p = reinterpret_cast<const float*>(ring.stage(s) + noise_off);
       nz.vec_ok = true;
-      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
     }
     if (NOISE == 1) ring_release(ring, s);
     if (tid == 0) {
@@ -494,7 +516,8 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
 template <typename T, int NT, int NOISE>
 __global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
-  __shared__ float s_red[4 * 32];
+  __shared__ float s_red[kRedFloats];
+  RedRing red{s_red, 0};
   float* srow = reinterpret_cast<float*>(dyn_smem);
   const int tid = threadIdx.x;
   SmemRow<T, NT> row;
@@ -508,12 +531,12 @@ __global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpPara
     if (NOISE == 2) {
       NoisePhilox nz;
       nz.key = p.key; nz.row = static_cast<uint32_t>(r); nz.off = p.off;
-      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
       nz.p = (NOISE == 1) ? p.noise + static_cast<size_t>(r) * p.K : nullptr;
       nz.vec_ok = false;
-      id = jump_row_math<NT, T>(row, p, c, nz, s_red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
     }
     if (tid == 0) {
       p.x_out[r] = id;

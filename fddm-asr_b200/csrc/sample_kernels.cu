@@ -230,13 +230,100 @@ struct JumpRowCtx {
   bool identity;
 };
 
+// The production sampling path: in-kernel RNG, temperature 1.  Per element it costs a max, an
+// exp2 + add, and a multiply + add; everything else is O(1) per thread:
+//   * softmax statistics in one (max, sum) block reduction, p_k = exp(z_k - m_t) * (exp(m_t - m) / S)
+//   * the un-normalised target weights are affine in p_k (exact: w_k = A_k (a_g p_k + b_g sum p),
+//     fast: w_k = abar p_k + (1-abar)/K), so a thread's mass follows from its sum of p_k, its element
+//     count and -- for the owner of x_t -- one correction; no second pass over the entries
+//   * hierarchical exponential race: the minimum of independent exponentials with rates w_k is
+//     Exp(sum w_k) and its argmin is categorical in w_k, independent of the minimum.  Each thread races
+//     once with its mass (one Exp(1) variate per thread instead of one per vocab entry) and the winning
+//     thread picks among its own entries by inverse CDF.
+template <int NT, typename T, class Row>
+__device__ __forceinline__ int jump_row_fast(Row& row, const JumpParams& p, const JumpRowCtx& c, const NoisePhilox& nz,
+                                             const float z_xt, RedRing& red, T* p_row_out, int* argmax_p) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
+  float m_t = kNegInf;
+  row.for_each([&](int, float& x) { m_t = fmaxf(m_t, x); });
+  const float nm_t = -m_t * kLog2e;
+  float s_t = 0.0f;
+  row.for_each([&](int, float& x) {
+    x = ex2_approx(fmaf(x, kLog2e, nm_t));
+    s_t += x;
+  });
+  float m = m_t, S = s_t;
+  block_softmax_stats<NT>(m, S, red);
+  const float inv_S = rcp_approx(S);
+  const float sc = ex2_approx((m_t - m) * kLog2e) * inv_S;
+  float psum = 0.0f;
+  if (argmax_p != nullptr) {
+    float pm = -1.0f;
+    int pm_k = 0x7fffffff;
+    row.for_each([&](int k, float& x) {
+      x = Vec16<T>::round_trip(x * sc);
+      psum += x;
+      if (x > pm) { pm = x; pm_k = k; }
+    });
+    block_argmax<NT>(pm, pm_k, red);
+    *argmax_p = pm_k;
+  } else {
+    row.for_each([&](int, float& x) {
+      x = Vec16<T>::round_trip(x * sc);
+      psum += x;
+    });
+  }
+  if (p.flags & FDDM_JUMP_WRITE_P) row.store(p_row_out, [](int, float x) { return x; });
+  if (c.identity) return c.xt;                                     // sched:133-134 (delta <= 0)
+
+  // w_k = wa_k * p_k + wb_k with (wa, wb) = (A a_g, A b_g sum_p) [exact] or (abar, (1-abar)/K) [fast]
+  const float xh_xt = Vec16<T>::round_trip(ex2_approx(fmaf(z_xt, kLog2e, -m * kLog2e)) * inv_S);
+  const float sum_p = S * inv_S;
+  float wa, wb, wa_x, wb_x;                                        // generic entry / the entry k == x_t
+  if (exact) {
+    const float bs = c.b_g * sum_p;                                // b_tgt * sum(x0hat)            sched:191
+    wa = c.b_c * c.a_g; wb = c.b_c * bs;                           // A = b_cum * sum_xt           sched:187
+    wa_x = (c.a_c + c.b_c) * c.a_g; wb_x = (c.a_c + c.b_c) * bs;   // A = a_cum + b_cum at x_t
+  } else {
+    wa = wa_x = c.ab;
+    wb = wb_x = (1.0f - c.ab) * p.u;                               // sampler:147-151
+  }
+  const bool owner = (row.owner_of(c.xt) == row.tid);
+  float mass = fmaf(wa, psum, wb * static_cast<float>(row.n_owned()));
+  if (owner) mass += fmaf(wa_x - wa, xh_xt, wb_x - wb);
+  const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(row.tid), nz.row, nz.off.x, nz.off.y), nz.key);
+  float best = __fdividef(mass, exp1_from_bits(rnd.x));
+  int best_k = row.tid;
+  block_argmax<NT>(best, best_k, red);
+  int picked = 0;
+  if (row.tid == best_k) {
+    const float target = mass * ((static_cast<float>(rnd.y >> 8) + 1.0f) * (1.0f / 16777216.0f));
+    float cum = 0.0f;
+    int chosen = -1, last_pos = c.xt;
+    row.for_each([&](int k, float& xh) {
+      const float w = (k == c.xt) ? fmaf(wa_x, xh, wb_x) : fmaf(wa, xh, wb);
+      if (chosen < 0 && w > 0.0f) {
+        cum += w;
+        last_pos = k;
+        if (cum >= target) chosen = k;
+      }
+    });
+    picked = (chosen < 0) ? last_pos : chosen;
+  }
+  return block_broadcast_int<NT>(row.tid == best_k, picked, red);
+}
+
 // One row: returns the new id (valid in every thread).  `NoiseT` provides E_k when sampling.
 template <int NT, typename T, class Row, class NoiseT>
 __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, const JumpRowCtx& c, const NoiseT& nz,
-                                             RedRing& red, T* p_row_out, int* argmax_p) {
+                                             const float z_xt, RedRing& red, T* p_row_out, int* argmax_p) {
   const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
   const bool sample = (p.flags & FDDM_JUMP_SAMPLE) != 0;
   const bool write_p = (p.flags & FDDM_JUMP_WRITE_P) != 0;
+  if constexpr (std::is_same<NoiseT, NoisePhilox>::value) {
+    if (sample && p.temperature == 1.0f) return jump_row_fast<NT, T>(row, p, c, nz, z_xt, red, p_row_out, argmax_p);
+  }
 
   // softmax in the logits dtype (F.softmax, sampler:189): exp(z-m)/S, rounded to T.
   // FAST (in-kernel RNG: the drawn ids cannot be compared with the reference's anyway) uses MUFU
@@ -488,6 +575,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     c.xt = mt.i0; c.identity = (mt.w == 0.0f);
     c.a_c = mt.f0; c.ab = mt.f0; c.b_c = mt.f1; c.a_g = mt.f2; c.b_g = mt.f3;
     row.load_from_smem(ring.stage(s), p.K, tid);
+    const float z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(ring.stage(s)) + c.xt);
     if (NOISE != 1) ring_release(ring, s);
     T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K : nullptr;
     int amax = 0;
@@ -495,12 +583,12 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     if (NOISE == 2) {
       NoisePhilox nz;
       nz.key = p.key; nz.row = static_cast<uint32_t>(mt.row); nz.off = p.off;
-      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
       nz.p = reinterpret_cast<const float*>(ring.stage(s) + noise_off);
       nz.vec_ok = true;
-      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     }
     if (NOISE == 1) ring_release(ring, s);
     if (tid == 0) {
@@ -525,18 +613,20 @@ __global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpPara
     JumpRowCtx c;
     jump_load_ctx(p, r, c);
     row.load_from_gmem(srow, static_cast<const T*>(p.logits) + static_cast<size_t>(r) * p.K, p.K, tid);
+    const float z_xt = srow[c.xt];
+    consumer_sync<NT>();                 // everyone has read z_xt before the row is overwritten in place
     T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(r) * p.K : nullptr;
     int amax = 0;
     int id;
     if (NOISE == 2) {
       NoisePhilox nz;
       nz.key = p.key; nz.row = static_cast<uint32_t>(r); nz.off = p.off;
-      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
       nz.p = (NOISE == 1) ? p.noise + static_cast<size_t>(r) * p.K : nullptr;
       nz.vec_ok = false;
-      id = jump_row_math<NT, T>(row, p, c, nz, red, p_row, p.argmax_p_out ? &amax : nullptr);
+      id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     }
     if (tid == 0) {
       p.x_out[r] = id;

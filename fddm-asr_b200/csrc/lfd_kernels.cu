@@ -93,57 +93,77 @@ __global__ void __launch_bounds__(256) lfd_tables_kernel(const double* __restric
 // Why the diagonal is done here on the CUDA cores: the tensor-core accumulator adds with truncation,
 // harmless for the zero-mean off-diagonal sums but a systematic ~1e-6 relative bias on the all-positive
 // diagonal sums when z_a and z_b are correlated -- and the loss is dominated by sum_j (1-C_jj)^2.
-// Mapping: warp -> chunk column (8 channels), lanes -> 32 consecutive rows: each lane reads 32 (16)
-// contiguous bytes of its row (whole sectors), the warp writes 512 contiguous bytes per plane.
-// grid = (D_pad/64, R_pad/256), 8 warps per CTA.
+// Layout change through shared memory: phase A reads a 32-row x 64-column tile row-contiguously
+// (256-byte runs, the standardisation is applied here), phase B has warp -> chunk column, lane -> row,
+// so every packed-plane store is a contiguous 512-byte run.  Rows are padded to 68 floats: both the
+// 16-byte stores of phase A and the 2 x 16-byte loads of phase B are bank-conflict free.
+// grid = (D_pad/64, R_pad/256); a CTA walks 8 row tiles and issues its 64 x 1 fp64 atomics once.
+constexpr int kPackLd = 68;
+
+template <typename T>
+__device__ __forceinline__ void pack_phase_a(const T* __restrict__ z, const float* __restrict__ scale,
+                                             const float* __restrict__ shift, int64_t r0, int c0, int64_t rows, int Tn,
+                                             int D, float (*tile)[kPackLd]) {
+  constexpr int N = Vec16<T>::N;                 // elements per 16-byte global vector
+  constexpr int VPR = 64 / N;                    // vectors per tile row
+  for (int idx = threadIdx.x; idx < 32 * VPR; idx += 256) {
+    const int row = idx / VPR, cv = idx % VPR;
+    const int64_t r = r0 + row;
+    const int c = c0 + cv * N;
+    float x[N];
+    if (r < rows && c < D) {
+      Vec16<T>::unpack(ldg_stream_v4(z + r * D + c), x);
+      const int64_t so = (r % Tn) * D + c;
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + so) + q);
+        const float4 h4 = __ldg(reinterpret_cast<const float4*>(shift + so) + q);
+        x[4 * q + 0] = fmaf(x[4 * q + 0], s4.x, h4.x); x[4 * q + 1] = fmaf(x[4 * q + 1], s4.y, h4.y);
+        x[4 * q + 2] = fmaf(x[4 * q + 2], s4.z, h4.z); x[4 * q + 3] = fmaf(x[4 * q + 3], s4.w, h4.w);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < N; ++e) x[e] = 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+      *reinterpret_cast<float4*>(&tile[row][cv * N + 4 * q]) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) lfd_pack_kernel(const T* __restrict__ za, const T* __restrict__ zb,
                                                        const float* __restrict__ tables, int64_t rows, int Tn, int D,
                                                        int64_t R_pad, __nv_bfloat16* __restrict__ a_hi,
                                                        __nv_bfloat16* __restrict__ a_lo, __nv_bfloat16* __restrict__ b_hi,
                                                        __nv_bfloat16* __restrict__ b_lo, double* __restrict__ diag) {
+  __shared__ __align__(16) float sA[32][kPackLd];
+  __shared__ __align__(16) float sB[32][kPackLd];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cc = blockIdx.x * 8 + warp;                      // chunk column
-  const int c0 = cc * 8;
+  const int c0 = blockIdx.x * 64;
+  const int cc = blockIdx.x * 8 + warp;                      // this warp's chunk column in phase B
   const int64_t TD = static_cast<int64_t>(Tn) * D;
-  const int64_t r_begin = static_cast<int64_t>(blockIdx.y) * 256;
   double acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.0;
-  const bool col_ok = c0 < D;
-#pragma unroll 2
   for (int it = 0; it < 8; ++it) {
-    const int64_t r = r_begin + it * 32 + lane;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 256 + it * 32;
+    pack_phase_a<T>(za, tables, tables + TD, r0, c0, rows, Tn, D, sA);
+    pack_phase_a<T>(zb, tables + 2 * TD, tables + 3 * TD, r0, c0, rows, Tn, D, sB);
+    __syncthreads();
     float a[8], b[8];
-    if (col_ok && r < rows) {
-      if (sizeof(T) == 4) {
-        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(za) + r * D + c0), a);
-        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(za) + r * D + c0 + 4), a + 4);
-        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(zb) + r * D + c0), b);
-        Vec16<float>::unpack(ldg_stream_v4(reinterpret_cast<const float*>(zb) + r * D + c0 + 4), b + 4);
-      } else {
-        Vec16<T>::unpack(ldg_stream_v4(za + r * D + c0), a);
-        Vec16<T>::unpack(ldg_stream_v4(zb + r * D + c0), b);
-      }
-      const int64_t so = (r % Tn) * D + c0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 sa = __ldg(reinterpret_cast<const float4*>(tables + so) + h);
-        const float4 ha = __ldg(reinterpret_cast<const float4*>(tables + TD + so) + h);
-        const float4 sb = __ldg(reinterpret_cast<const float4*>(tables + 2 * TD + so) + h);
-        const float4 hb = __ldg(reinterpret_cast<const float4*>(tables + 3 * TD + so) + h);
-        a[4 * h + 0] = fmaf(a[4 * h + 0], sa.x, ha.x); a[4 * h + 1] = fmaf(a[4 * h + 1], sa.y, ha.y);
-        a[4 * h + 2] = fmaf(a[4 * h + 2], sa.z, ha.z); a[4 * h + 3] = fmaf(a[4 * h + 3], sa.w, ha.w);
-        b[4 * h + 0] = fmaf(b[4 * h + 0], sb.x, hb.x); b[4 * h + 1] = fmaf(b[4 * h + 1], sb.y, hb.y);
-        b[4 * h + 2] = fmaf(b[4 * h + 2], sb.z, hb.z); b[4 * h + 3] = fmaf(b[4 * h + 3], sb.w, hb.w);
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += static_cast<double>(a[e]) * static_cast<double>(b[e]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { a[e] = 0.0f; b[e] = 0.0f; }
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[lane][warp * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[lane][warp * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sB[lane][warp * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sB[lane][warp * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
     }
-    const int64_t off = (static_cast<int64_t>(cc) * R_pad + r) * 8;       // elements
+    __syncthreads();                                         // tiles are rewritten by the next iteration
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += static_cast<double>(a[e]) * static_cast<double>(b[e]);   // pads are 0
+    const int64_t off = (static_cast<int64_t>(cc) * R_pad + r0 + lane) * 8;                        // elements
     const uint4 ah = Vec16<__nv_bfloat16>::pack(a), bh = Vec16<__nv_bfloat16>::pack(b);
     stg_stream_v4(a_hi + off, ah);
     stg_stream_v4(b_hi + off, bh);
@@ -159,13 +179,13 @@ __global__ void __launch_bounds__(256) lfd_pack_kernel(const T* __restrict__ za,
       stg_stream_v4(b_lo + off, Vec16<__nv_bfloat16>::pack(t));
     }
   }
-  if (col_ok) {
+  if (cc * 8 < D) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       double v = acc[e];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) atomicAdd(diag + c0 + e, v);
+      if (lane == 0) atomicAdd(diag + cc * 8 + e, v);
     }
   }
 }
@@ -251,13 +271,22 @@ __global__ void __launch_bounds__(256) lfd_loss_kernel(const float* __restrict__
     s_last = (atomicAdd(&counters[0], 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last) {                                        // fixed-order tree over the per-CTA partials
     __threadfence();
     double t = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(&partials[b]);   // fixed order
-    *loss_out = static_cast<float>(t);
-    counters[0] = 0;
-    __threadfence();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(&partials[b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < 8; ++w) tot += s_red[w];
+      *loss_out = static_cast<float>(tot);
+      counters[0] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -312,6 +341,10 @@ __global__ void __launch_bounds__(256) lfd_bn_reduce_kernel(const T* __restrict_
 }
 
 // dx = (dz~ - mean_b dz~ - z~ * mean_b(dz~ z~)) * rstd * upstream      (batch-norm backward)
+// Per (t,d) the expression is affine in (dz~, x):  dx = A*dz~ + Bx*x + C  with
+//   A = rstd*up,  Bx = -rstd^2 * m2 * up,  C = -(m1 + shift*m2) * rstd * up     (z~ = x*rstd + shift)
+// so a thread owns one 16-byte vector of the (t,d) plane, computes its coefficients once and streams
+// over the batch (same shape as the stats kernel).  grid = (ceil(TD/N/256), 2, bsplit).
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) lfd_bn_finalize_kernel(const T* __restrict__ za, const T* __restrict__ zb,
                                                               const float* __restrict__ dza,
@@ -319,19 +352,56 @@ __global__ void __launch_bounds__(256) lfd_bn_finalize_kernel(const T* __restric
                                                               const float* __restrict__ tables,
                                                               const double* __restrict__ bn, double inv_nb,
                                                               const float* __restrict__ grad_scale, int B, int64_t TD,
-                                                              T* __restrict__ oa, T* __restrict__ ob) {
+                                                              int bsplit, T* __restrict__ oa, T* __restrict__ ob) {
   constexpr int N = VEC ? Vec16<T>::N : 1;
+  const int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v * N >= TD) return;
   const int which = blockIdx.y;
   const T* z = which == 0 ? za : zb;
   const float* dz = which == 0 ? dza : dzb;
   T* out = which == 0 ? oa : ob;
   const float up = grad_scale ? __ldg(grad_scale) : 1.0f;
-  const int64_t nvec_plane = (TD + N - 1) / N;
-  const int64_t total = static_cast<int64_t>(B) * nvec_plane;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t b = i / nvec_plane, v = i - b * nvec_plane;
-    const int64_t td = v * N, off = b * TD + td;
+  float cA[N], cB[N], cC[N];
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+    const int64_t td = v * N + e;
+    const float sc = tables[which * 2 * TD + td], sh = tables[which * 2 * TD + TD + td];
+    const float m1 = static_cast<float>(bn[which * 2 * TD + td] * inv_nb);
+    const float m2 = static_cast<float>(bn[which * 2 * TD + TD + td] * inv_nb);
+    cA[e] = sc * up;
+    cB[e] = -sc * sc * m2 * up;
+    cC[e] = -(m1 + sh * m2) * sc * up;
+  }
+  const int bchunk = (B + bsplit - 1) / bsplit;
+  const int b0 = blockIdx.z * bchunk, b1 = min(B, b0 + bchunk);
+  constexpr int U = 2;
+  int b = b0;
+  for (; b + U <= b1; b += U) {
+    float x[U][N], g[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t off = static_cast<int64_t>(b + u) * TD + v * N;
+      if (VEC) {
+        Vec16<T>::unpack(ldg_stream_v4(z + off), x[u]);
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) Vec16<float>::unpack(ldg_stream_v4(dz + off + 4 * q), g[u] + 4 * q);
+      } else {
+        x[u][0] = Vec16<T>::load1(z + off);
+        g[u][0] = dz[off];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t off = static_cast<int64_t>(b + u) * TD + v * N;
+      float o[N];
+#pragma unroll
+      for (int e = 0; e < N; ++e) o[e] = fmaf(cA[e], g[u][e], fmaf(cB[e], x[u][e], cC[e]));
+      if (VEC) stg_stream_v4(out + off, Vec16<T>::pack(o));
+      else Vec16<T>::store1(out + off, o[0]);
+    }
+  }
+  for (; b < b1; ++b) {
+    const int64_t off = static_cast<int64_t>(b) * TD + v * N;
     float x[N], g[N], o[N];
     if (VEC) {
       Vec16<T>::unpack(ldg_stream_v4(z + off), x);
@@ -342,13 +412,7 @@ __global__ void __launch_bounds__(256) lfd_bn_finalize_kernel(const T* __restric
       g[0] = dz[off];
     }
 #pragma unroll
-    for (int e = 0; e < N; ++e) {
-      const float sc = tables[which * 2 * TD + td + e], sh = tables[which * 2 * TD + TD + td + e];
-      const float m1 = static_cast<float>(bn[which * 2 * TD + td + e] * inv_nb);
-      const float m2 = static_cast<float>(bn[which * 2 * TD + TD + td + e] * inv_nb);
-      const float zt = fmaf(x[e], sc, sh);
-      o[e] = (g[e] - m1 - zt * m2) * sc * up;
-    }
+    for (int e = 0; e < N; ++e) o[e] = fmaf(cA[e], g[e], fmaf(cB[e], x[e], cC[e]));
     if (VEC) stg_stream_v4(out + off, Vec16<T>::pack(o));
     else Vec16<T>::store1(out + off, o[0]);
   }
@@ -429,15 +493,18 @@ int launch_finalize(const void* za, const void* zb, int dtype, int64_t B, int64_
                     void* oa, void* ob, cudaStream_t stream) {
   const bool vec = vec_ok(za, zb, dtype, TD) && TD % 8 == 0 && reinterpret_cast<uintptr_t>(oa) % 16 == 0 &&
                    reinterpret_cast<uintptr_t>(ob) % 16 == 0;
-  dim3 grid(static_cast<unsigned>(num_sms() * 8), 2, 1);
+  const int n = vec ? Vec16<T>::N : 1;
+  const int64_t nthr = (TD + n - 1) / n;
+  const int bsplit = pick_bsplit(nthr, B);
+  dim3 grid(static_cast<unsigned>((nthr + 255) / 256), 2, bsplit);
   if (vec)
     lfd_bn_finalize_kernel<T, true><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb), dza,
                                                               dzb, tables, bn, inv_nb, grad_scale, static_cast<int>(B),
-                                                              TD, static_cast<T*>(oa), static_cast<T*>(ob));
+                                                              TD, bsplit, static_cast<T*>(oa), static_cast<T*>(ob));
   else
     lfd_bn_finalize_kernel<T, false><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb),
                                                                dza, dzb, tables, bn, inv_nb, grad_scale,
-                                                               static_cast<int>(B), TD, static_cast<T*>(oa),
+                                                               static_cast<int>(B), TD, bsplit, static_cast<T*>(oa),
                                                                static_cast<T*>(ob));
   FDDM_LAUNCH_OK();
   return FDDM_OK;

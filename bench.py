@@ -212,7 +212,8 @@ def run_gpu(args):
     d["logits"].requires_grad_(True); d["za"].requires_grad_(True); d["zb"].requires_grad_(True)
 
     sch = fb.DiscreteDiffusionScheduler(K=V, T=T_TRAIN, device=dev)
-    ad = fb.SchedulerAdapter(sch, group=group)
+    # multi-GPU: the KL scalar is folded into the one scalar all-reduce at the end of the step
+    ad = fb.SchedulerAdapter(sch, group=group, defer_reduce=True)
     dec = ResidentDecoder()
     smp = fb.DiffusionJumpySampler(sch, dec, K=V, T_train=T_TRAIN, T_infer=T_INFER, r=R_JUMP, greedy=False,
                                    sampling_mode="exact", device=dev)
@@ -222,6 +223,10 @@ def run_gpu(args):
     def step(dd, timed_kl=False):
         for k in ("logits", "za", "zb"):
             dd[k].grad = None
+        # (overlapping the all-reduces with the persistent row kernels on a side stream was measured at N=8
+        #  and is slower -- the collective's CTAs wait on peers while holding SMs -- so they stay in order)
+        lfd_op = fb.LfdPipeline(dd["za"], dd["zb"], LAMBDA, group=group, overlap=False)
+        lfd_op.stats()                                            # + all-reduce of the batch statistics
         xt = ad.sample_q(dd["x0"], dd["t"])
         if timed_kl:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,11 +234,14 @@ def run_gpu(args):
         kl = ad.kl_term(xt, dd["x0"], dd["logits"], dd["t"], dd["mask"])
         if timed_kl:
             e1.record(); kl_ev.append((e0, e1))
+        lfd_op.xcov(piggyback=kl if world > 1 else None)          # + all-reduce of the covariance (carrying the KL partial sum)
         dec.logits = dd["logits"].detach()
         x_new, _ = smp._jump_once(dd["x0"], T_INFER, R_JUMP, cond, L, want_p=False)
-        lfd = fb.lfd_loss(dd["za"], dd["zb"], LAMBDA, group=group)
+        lfd = lfd_op.loss()
         total = kl + TAU * ad.w_t(dd["t"]).mean() * lfd.float()
         total.backward()
+        if world > 1:                                             # reported loss: global KL rode along with the covariance
+            total = lfd_op.piggyback + (total.detach() - kl.detach())
         return total, x_new
 
     def sync_all():
@@ -259,8 +267,10 @@ def run_gpu(args):
     n0 = fb._lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         total, x_new = step(d, timed_kl=True)
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps       # CPU time to enqueue one step (no sync)
     ev1.record()
     sync_all()
     launches = fb._lib.launch_count() - n0
@@ -332,7 +342,7 @@ def run_gpu(args):
                        "l2": f"inputs {h2d / 1e6:.0f} MB/step > 126 MB L2 (no flush needed)"},
             "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 4),
             "clocks": clk,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -11,7 +11,7 @@ from . import _lib
 from .scheduler import DiscreteDiffusionScheduler
 from .adapter import SchedulerAdapter
 from .sampler import DiffusionJumpySampler, ModelAdapter
-from .losses import lfd_loss
+from .losses import LfdPipeline, lfd_loss
 
-__all__ = ["DiscreteDiffusionScheduler", "SchedulerAdapter", "DiffusionJumpySampler", "ModelAdapter", "lfd_loss",
+__all__ = ["DiscreteDiffusionScheduler", "SchedulerAdapter", "DiffusionJumpySampler", "ModelAdapter", "lfd_loss", "LfdPipeline",
            "_lib"]

@@ -70,16 +70,20 @@ class _KLTermFn(torch.autograd.Function):
 
 
 class SchedulerAdapter:
-    def __init__(self, scheduler: DiscreteDiffusionScheduler, *, grad_scale=None, group=None):
+    def __init__(self, scheduler: DiscreteDiffusionScheduler, *, grad_scale=None, group=None,
+                 defer_reduce: bool = False):
         """`grad_scale`: optional fp32 device scalar (or a zero-argument callable returning one),
         the upstream gradient the training loop will feed into `kl_term` (e.g. the AMP GradScaler's
         scale); folding it into the fused pass avoids a second pass over the gradient.
         `group`: optional torch.distributed process group; when given the batch is taken to be
         sharded over its ranks, the batch mean uses the global batch size and the scalar loss is
-        all-reduced (SUM) -- the only collective of the KL path."""
+        all-reduced (SUM) -- the only collective of the KL path.  `defer_reduce=True` skips that
+        all-reduce: kl_term then returns this rank's partial sum / global batch (its gradient is already
+        the global loss's gradient), for callers that fold the scalar into a later collective."""
         self.sch = scheduler
         self._grad_scale = grad_scale
         self._group = group
+        self._defer = bool(defer_reduce)
 
     # -- train.py:180-188 ------------------------------------------------------------------------
     def sample_q(self, x0: torch.Tensor, t: torch.Tensor, *, exp_noise=None, generator=None) -> torch.Tensor:
@@ -109,7 +113,8 @@ class SchedulerAdapter:
         gs = self._grad_scale() if callable(self._grad_scale) else self._grad_scale
         if gs is not None:
             gs = gs.detach().to(device=dev, dtype=torch.float32).reshape(())
-        return _KLTermFn.apply(logits, xt, x0, t, mask, betas, int(betas.numel()), B * world, gs, self._group)
+        return _KLTermFn.apply(logits, xt, x0, t, mask, betas, int(betas.numel()), B * world, gs,
+                               None if self._defer else self._group)
 
     # -- train.py:257-273 ------------------------------------------------------------------------
     def w_t(self, t: torch.Tensor) -> torch.Tensor:

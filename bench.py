@@ -219,6 +219,10 @@ def run_gpu(args):
                                    sampling_mode="exact", device=dev)
     cond = torch.zeros(B, 1, 1, device=dev)
     kl_ev = []
+    # device-side Philox {seed, offset}: read by the kernels, advanced by a (captured) add each step, so
+    # that a CUDA-graph replay draws fresh noise exactly like an eager step would
+    pstate = torch.tensor([1337 + rank, 0], dtype=torch.int64, device=dev)
+    smp.philox_state = pstate
 
     def step(dd, timed_kl=False):
         for k in ("logits", "za", "zb"):
@@ -227,7 +231,8 @@ def run_gpu(args):
         #  and is slower -- the collective's CTAs wait on peers while holding SMs -- so they stay in order)
         lfd_op = fb.LfdPipeline(dd["za"], dd["zb"], LAMBDA, group=group, overlap=False)
         lfd_op.stats()                                            # + all-reduce of the batch statistics
-        xt = ad.sample_q(dd["x0"], dd["t"])
+        pstate[1:].add_(8)
+        xt = ad.sample_q(dd["x0"], dd["t"], philox_state=pstate)
         if timed_kl:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -264,18 +269,61 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step(d)
     sync_all()
+    # The step is ~30 short launches (0.9 ms of device time, 0.6 ms of host time to enqueue -- more when 8
+    # ranks share one host), so the whole step (forward, collectives, backward) is captured once in a CUDA
+    # graph and replayed: every library call is stream-ordered and sync-free by contract.
+    graph = None
+    launches_per_step = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(d)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            sync_all()
+            graph = torch.cuda.CUDAGraph()
+            n0 = fb._lib.launch_count()
+            with torch.cuda.graph(graph):
+                g_total, g_xnew = step(d)
+            launches_per_step = fb._lib.launch_count() - n0
+            graph.replay()
+            sync_all()
+        except Exception as e:                                    # report and fall back to eager launches
+            if rank == 0:
+                print(f"bench.py: CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize(dev)
     n0 = fb._lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     h0 = time.perf_counter()
     for _ in range(args.steps):
-        total, x_new = step(d, timed_kl=True)
+        if graph is not None:
+            graph.replay()
+        else:
+            total, x_new = step(d, timed_kl=True)
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps       # CPU time to enqueue one step (no sync)
     ev1.record()
     sync_all()
-    launches = fb._lib.launch_count() - n0
+    if graph is not None:
+        total, x_new = g_total, g_xnew
+        launches = launches_per_step * args.steps
+        # the dominant kernel timed on its own stream position, eagerly, over the same number of launches
+        # (back to back between one pair of events, so the queue never drains while the host prepares a call)
+        xt_k = ad.sample_q(d["x0"], d["t"], philox_state=pstate)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            ad.kl_term(xt_k, d["x0"], d["logits"], d["t"], d["mask"])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        kl_batch_ms = e0.elapsed_time(e1) / args.steps
+    else:
+        launches = fb._lib.launch_count() - n0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    kl_ms = sum(a.elapsed_time(b) for a, b in kl_ev) / max(1, len(kl_ev))
+    kl_ms = kl_batch_ms if graph is not None else sum(a.elapsed_time(b) for a, b in kl_ev) / max(1, len(kl_ev))
     elems = B * L * V                                            # per GPU per step
     ms_step = ms_total / args.steps
     value = world * elems / (ms_step * 1e-3) / 1e9
@@ -343,6 +391,7 @@ def run_gpu(args):
             "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 4),
+            "cuda_graph": graph is not None,
             "clocks": clk,
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -385,6 +434,7 @@ def main():
     ap.add_argument("--workload", default="c5shard", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

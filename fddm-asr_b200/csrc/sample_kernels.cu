@@ -55,6 +55,17 @@ struct NoisePhilox {        // counter = (k/4 within the row, row, offset); lane
   }
 };
 
+// (seed, offset) either from the launch parameters or, when a device pointer is given, from device
+// memory -- so that a captured CUDA graph draws fresh noise on every replay
+__device__ __forceinline__ void philox_key_off(const uint64_t* state, uint2 key_in, uint2 off_in, uint2& key, uint2& off) {
+  key = key_in; off = off_in;
+  if (state != nullptr) {
+    const uint64_t sd = state[0], of = state[1];
+    key = make_uint2(static_cast<uint32_t>(sd), static_cast<uint32_t>(sd >> 32));
+    off = make_uint2(static_cast<uint32_t>(of), static_cast<uint32_t>(of >> 32));
+  }
+}
+
 // f(k, x&, E_k) over a RegRow / SmemRow
 template <typename T, int NT, int EPT, class Noise, class F>
 __device__ __forceinline__ void for_each_noise(RegRow<T, NT, EPT>& row, const Noise& nz, F&& f) {
@@ -89,6 +100,7 @@ struct SampleQParams {
   int T, L, K, rows;
   float eps, u;              // u = fp32(1/K)  (sched:45)
   uint2 key, off;
+  const uint64_t* philox_state;   // optional device {seed, offset}: overrides key/off (CUDA-graph replay)
 };
 
 // the two values of the q_sample row for one-hot x0, with the reference's roundings (sched:44-49)
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(NT) sample_q_kernel(const SampleQParams p) {
       if (sc > best) { best = sc; best_k = k; }                    // strict: earlier index keeps ties
     };
     NoisePhilox ph;
-    ph.key = p.key; ph.row = static_cast<uint32_t>(row); ph.off = p.off;
+    philox_key_off(p.philox_state, p.key, p.off, ph.key, ph.off); ph.row = static_cast<uint32_t>(row);
     const float* nrow = PHILOX ? nullptr : p.noise + static_cast<size_t>(row) * p.K;
     if (vec) {
       const int nvec = p.K / 4;
@@ -180,7 +192,9 @@ __global__ void __launch_bounds__(256) sample_q_closed_kernel(const SampleQParam
   float p_hi, p_lo;
   q_sample_two_values(p.alpha_bar[tt - 1], p.u, p.eps, p.K, p_hi, p_lo);
   const int x0 = static_cast<int>(p.x0[row]);
-  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(row), 0u, p.off.x, p.off.y), p.key);
+  uint2 key, off;
+  philox_key_off(p.philox_state, p.key, p.off, key, off);
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(row), 0u, off.x, off.y), key);
   const float u1 = static_cast<float>(r.x >> 8) * (1.0f / 16777216.0f);             // [0,1)
   int out = x0;
   if (!(u1 < p_hi) && p.K > 1) {
@@ -215,6 +229,7 @@ struct JumpParams {
   int abar_index;
   float temperature, eps, u;
   uint2 key, off;
+  const uint64_t* philox_state;   // optional device {seed, offset}: overrides key/off (CUDA-graph replay)
 };
 int jump_launch_f32(const JumpParams& p, int noise, cudaStream_t stream);
 int jump_launch_bf16(const JumpParams& p, int noise, cudaStream_t stream);
@@ -582,7 +597,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     int id;
     if (NOISE == 2) {
       NoisePhilox nz;
-      nz.key = p.key; nz.row = static_cast<uint32_t>(mt.row); nz.off = p.off;
+      philox_key_off(p.philox_state, p.key, p.off, nz.key, nz.off); nz.row = static_cast<uint32_t>(mt.row);
       id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
@@ -620,7 +635,7 @@ __global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpPara
     int id;
     if (NOISE == 2) {
       NoisePhilox nz;
-      nz.key = p.key; nz.row = static_cast<uint32_t>(r); nz.off = p.off;
+      philox_key_off(p.philox_state, p.key, p.off, nz.key, nz.off); nz.row = static_cast<uint32_t>(r);
       id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
@@ -704,8 +719,8 @@ int FDDM_JUMP_FN(const JumpParams& p, int noise, cudaStream_t stream) {
 extern "C" {
 
 int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_bar, int64_t T, int64_t B, int64_t L,
-                      int64_t K, float eps, const float* exp_noise, uint64_t seed, uint64_t offset, int64_t* xt_out,
-                      fddm_stream_t stream_) {
+                      int64_t K, float eps, const float* exp_noise, uint64_t seed, uint64_t offset,
+                      const uint64_t* philox_state, int64_t* xt_out, fddm_stream_t stream_) {
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(x0 && t && alpha_bar && xt_out, "sample_q_ids: null pointer argument");
@@ -719,6 +734,7 @@ int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_ba
   p.u = static_cast<float>(1.0 / static_cast<double>(K));
   p.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   p.off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
+  p.philox_state = philox_state;
   if (exp_noise) {
     const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(num_sms()) * 8));
     sample_q_kernel<256, false><<<grid, 256, 0, stream>>>(p);
@@ -731,8 +747,8 @@ int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_ba
 
 int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const float* coeffs, const float* alpha_bar,
                    int64_t abar_index, int64_t B, int64_t L, int64_t K, int flags, float temperature, float eps,
-                   const float* exp_noise, uint64_t seed, uint64_t offset, void* workspace, int64_t* x_out,
-                   int64_t* argmax_p_out, void* p_x0_out, fddm_stream_t stream_) {
+                   const float* exp_noise, uint64_t seed, uint64_t offset, const uint64_t* philox_state,
+                   void* workspace, int64_t* x_out, int64_t* argmax_p_out, void* p_x0_out, fddm_stream_t stream_) {
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(logits && x_t && x_out, "jump_step: null pointer argument");
@@ -757,6 +773,7 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
   p.u = static_cast<float>(1.0 / static_cast<double>(K));
   p.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   p.off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
+  p.philox_state = philox_state;
   const bool sample = (flags & FDDM_JUMP_SAMPLE) != 0;
   const int noise = !sample ? 0 : (exp_noise ? 1 : 2);
   if (dtype == FDDM_F32) return jump_launch_f32(p, noise, stream);

@@ -42,7 +42,7 @@ SIGNATURES = {
     "fddm_last_error": (C.c_char_p, []),
     "fddm_launch_count": (_i64, []),
     "fddm_q_sample_dense": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp]),
-    "fddm_sample_q_ids": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _u64, _u64, _vp, _vp]),
+    "fddm_sample_q_ids": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _u64, _u64, _vp, _vp, _vp]),
     "fddm_q_posterior_dense": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp]),
     "fddm_multistep_coeffs": (_i32, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp]),
     "fddm_q_posterior_multi_dense": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp, _vp]),
@@ -52,7 +52,7 @@ SIGNATURES = {
                                         _vp, _vp, _vp]),
     "fddm_scale_inplace": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "fddm_jump_step": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _f32, _vp, _u64, _u64,
-                              _vp, _vp, _vp, _vp, _vp]),
+                              _vp, _vp, _vp, _vp, _vp, _vp]),
     "fddm_lfd_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64]),
     "fddm_lfd_stats": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp]),
     "fddm_lfd_xcov": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _f64, _f32, _vp, _vp, _vp]),

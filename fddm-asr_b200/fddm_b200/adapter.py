@@ -86,8 +86,9 @@ class SchedulerAdapter:
         self._defer = bool(defer_reduce)
 
     # -- train.py:180-188 ------------------------------------------------------------------------
-    def sample_q(self, x0: torch.Tensor, t: torch.Tensor, *, exp_noise=None, generator=None) -> torch.Tensor:
-        return self.sch.sample_q_ids(x0, t, exp_noise=exp_noise, generator=generator)
+    def sample_q(self, x0: torch.Tensor, t: torch.Tensor, *, exp_noise=None, generator=None,
+                 philox_state=None) -> torch.Tensor:
+        return self.sch.sample_q_ids(x0, t, exp_noise=exp_noise, generator=generator, philox_state=philox_state)
 
     # -- train.py:190-255 ------------------------------------------------------------------------
     def kl_term(self, xt: torch.Tensor, x0: torch.Tensor, logits_x0: torch.Tensor, t: torch.Tensor,

@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from . import _lib as L
-from .scheduler import philox_state
+from .scheduler import philox_seed_offset
 
 
 class ModelAdapter:
@@ -56,6 +56,9 @@ class DiffusionJumpySampler:
         # parity-test hook: callable(step_index, (B, L, K)) -> fp32 Exp(1) noise tensor, or None
         self.noise_fn = None
         self.generator: Optional[torch.Generator] = None
+        # optional int64[2] device tensor {seed, offset} read by the kernel instead of the host-side
+        # generator state (the caller advances the offset): makes a jump replayable in a CUDA graph
+        self.philox_state: Optional[torch.Tensor] = None
 
     # sampler:219-236, including the 0-based table indexed by a 1-based train-axis index (Q3)
     def _alpha_bar_index(self, t_infer_scalar: int) -> int:
@@ -122,8 +125,8 @@ class DiffusionJumpySampler:
                 noise = noise.to(device=dev, dtype=torch.float32).contiguous()
                 if noise.numel() != B * Lq * self.K:
                     raise ValueError("injected noise must have B*L*K elements")
-            else:
-                seed, offset = philox_state(dev, self.generator, 4)
+            elif self.philox_state is None:
+                seed, offset = philox_seed_offset(dev, self.generator, 4)
         p_x0 = None
         if want_p:
             flags |= L.JUMP_WRITE_P
@@ -133,7 +136,8 @@ class DiffusionJumpySampler:
         ws = L.zeroed_workspace(dev, "jump", L.JUMP_WORKSPACE_BYTES)
         L.check(L.lib.fddm_jump_step(logits.data_ptr(), dt, x_t.data_ptr(), L.ptr(coeffs), L.ptr(alpha_bar),
                                      abar_index, B, Lq, self.K, flags, self.temperature, eps, L.ptr(noise), seed,
-                                     offset, ws.data_ptr(), x_out.data_ptr(), L.ptr(amax), L.ptr(p_x0),
+                                     offset, L.ptr(self.philox_state if (sample and noise is None) else None),
+                                     ws.data_ptr(), x_out.data_ptr(), L.ptr(amax), L.ptr(p_x0),
                                      L.stream_ptr(dev)), "jump_step")
         return x_out, p_x0, amax
 

@@ -107,11 +107,14 @@ class DiscreteDiffusionScheduler:
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def sample_q_ids(self, x0: torch.Tensor, t: torch.Tensor, *, exp_noise: Optional[torch.Tensor] = None,
-                     generator: Optional[torch.Generator] = None) -> torch.Tensor:
+                     generator: Optional[torch.Generator] = None,
+                     philox_state: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Fused ids -> ids forward corruption == one-hot -> q_sample -> torch.multinomial(.,1)
         (train.py:180-188) without materialising the [B,L,K] one-hot / probability tensors.
         `exp_noise`: optional injected Exp(1) variates fp32 [B,L,K] (parity tests); otherwise
-        in-kernel Philox keyed by the torch CUDA generator's (seed, offset)."""
+        in-kernel Philox keyed by the torch CUDA generator's (seed, offset), or by `philox_state`, an
+        int64[2] device tensor {seed, offset} read by the kernel (the caller advances the offset; this
+        is what makes the call replayable inside a CUDA graph)."""
         if x0.dim() != 2:
             raise ValueError(f"x0 must be (B, L) token ids, got shape {tuple(x0.shape)}")
         x0 = x0.long().contiguous()
@@ -126,16 +129,16 @@ class DiscreteDiffusionScheduler:
                 raise ValueError("exp_noise must be float32 with B*L*K elements")
             exp_noise = exp_noise.contiguous()
             L.require_cuda(exp_noise, x0)
-        else:
-            seed, offset = philox_state(dev, generator, 4 * ((self.K + 3) // 4))
+        elif philox_state is None:
+            seed, offset = philox_seed_offset(dev, generator, 4)
         out = torch.empty_like(x0)
         L.check(L.lib.fddm_sample_q_ids(x0.data_ptr(), t.data_ptr(), self.alpha_bar.data_ptr(), self.T, B, Lq,
-                                        self.K, self.eps, L.ptr(exp_noise), seed, offset, out.data_ptr(),
-                                        L.stream_ptr(dev)), "sample_q_ids")
+                                        self.K, self.eps, L.ptr(exp_noise), seed, offset, L.ptr(philox_state),
+                                        out.data_ptr(), L.stream_ptr(dev)), "sample_q_ids")
         return out
 
 
-def philox_state(device: torch.device, generator: Optional[torch.Generator], increment: int):
+def philox_seed_offset(device: torch.device, generator: Optional[torch.Generator], increment: int):
     """(seed, offset) of the torch CUDA generator, advancing its offset so successive calls draw
     independent streams (same contract as ATen's philox_cuda_state)."""
     idx = device.index if device.index is not None else torch.cuda.current_device()

@@ -40,7 +40,7 @@ typedef enum {
 } fddm_status_t;
 
 #define FDDM_MAX_VOCAB 49152       /* one fp32 row must fit the 227 KB shared memory of an SM */
-#define FDDM_ABI_VERSION 1
+#define FDDM_ABI_VERSION 2
 
 /* jump_step flags */
 #define FDDM_JUMP_EXACT   0x1      /* sampling_mode == "exact" (else "fast"), sampler:192-209 */
@@ -62,11 +62,15 @@ int fddm_q_sample_dense(const float* x0_prob, const int64_t* t, const float* alp
 /* ------------------------------------------------------------------------------------------------
  * a3  SchedulerAdapter.sample_q  (ids -> ids, the one-hot is never materialised)  train:180-188
  *   xt = argmax_k q_sample(onehot(x0), t)_k / E_k         ( == torch.multinomial(p, 1) )
- * exp_noise: fp32 [B*L, K] of Exp(1) variates, or NULL to draw them in-kernel with Philox4x32-10
- * keyed by (seed, offset).  Ties -> lowest index. */
+ * exp_noise: fp32 [B*L, K] of Exp(1) variates (the per-entry race replays torch.multinomial bit for
+ * bit), or NULL to draw in-kernel with Philox4x32-10 keyed by (seed, offset): the row of q_sample is
+ * two-valued for a one-hot x0, so the draw is O(1) per token (keep x0 with probability p_hi, else a
+ * uniform other id).  philox_state: optional device uint64[2] = {seed, offset} that overrides the two
+ * scalars (so a captured CUDA graph draws fresh noise on every replay).  Ties -> lowest index. */
 int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_bar, int64_t T,
                       int64_t B, int64_t L, int64_t K, float eps, const float* exp_noise,
-                      uint64_t seed, uint64_t offset, int64_t* xt_out, fddm_stream_t stream);
+                      uint64_t seed, uint64_t offset, const uint64_t* philox_state, int64_t* xt_out,
+                      fddm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a4  DiscreteDiffusionScheduler.q_posterior                                  sched:52-104
@@ -133,7 +137,9 @@ int fddm_scale_inplace(void* x, int dtype, int64_t n, const float* num, const fl
  *   alpha_bar    fast mode: table [T]; abar_index = the (quirk-Q3, 0-based) table index to use, or
  *                -1 for alpha-bar = 1 (target step <= 0)                       sampler:219-236
  *   temperature  used only when sampling and != 1                              sampler:159-161
- *   exp_noise    fp32 [B*L, K] Exp(1) variates or NULL -> in-kernel Philox (seed, offset)
+ *   exp_noise    fp32 [B*L, K] Exp(1) variates (per-entry race, bit-faithful arithmetic) or NULL ->
+ *                in-kernel Philox (seed, offset) or device {seed, offset} in philox_state: hierarchical
+ *                exponential race, one variate per thread, MUFU arithmetic
  *   workspace    FDDM_JUMP_WORKSPACE_BYTES bytes, zero-initialised ONCE by the caller (row scheduler)
  *   argmax_p_out optional int64 [B,L]: argmax_k p_x0 -- the sampler's final x_0 (sampler:292), fused
  *                here so the last p_x0 is never re-read
@@ -142,8 +148,8 @@ int fddm_scale_inplace(void* x, int dtype, int64_t n, const float* num, const fl
 int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const float* coeffs,
                    const float* alpha_bar, int64_t abar_index, int64_t B, int64_t L, int64_t K,
                    int flags, float temperature, float eps, const float* exp_noise, uint64_t seed,
-                   uint64_t offset, void* workspace, int64_t* x_out, int64_t* argmax_p_out,
-                   void* p_x0_out, fddm_stream_t stream);
+                   uint64_t offset, const uint64_t* philox_state, void* workspace, int64_t* x_out,
+                   int64_t* argmax_p_out, void* p_x0_out, fddm_stream_t stream);
 /* ------------------------------------------------------------------------------------------------
  * a8  lfd_loss                                                                losses:18-58
  * z_a, z_b: [B,T,D] dtype `dtype` (this rank's batch shard); rows = B*T.  Phases are separate entry

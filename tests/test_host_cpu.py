@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol():
 def test_host_only_entry_points():
     import fddm_b200
     lib = fddm_b200._lib.lib
-    assert lib.fddm_version() == 1
+    assert lib.fddm_version() == 2
     assert lib.fddm_kl_workspace_bytes(32, 128) >= 128 + 32 * 128 * 4
     assert lib.fddm_kl_workspace_bytes(0, 5) == 0
     w = lib.fddm_lfd_workspace_bytes(32, 128, 768)

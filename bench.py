@@ -383,8 +383,16 @@ def run_gpu(args):
     valid_rows = int(host["mask"].sum())
     algo_bytes = float(s_bytes) * V * (valid_rows + B * L)
     achieved = algo_bytes / (kl_ms * 1e-3) / 1e9
+    traffic = None                                                # dram bytes per launch from the committed ncu capture
+    try:
+        if args.workload == "c5shard" and args.dtype == "f32":
+            with open(os.path.join(ROOT, "profiles", "r01b_kl_traffic.json")) as f:
+                traffic = float(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": "kl_rows_ring_kernel (fused KL forward+backward)", "achieved": round(achieved, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_source": "profiles/r01b_kl_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": algo_bytes, "valid_row_fraction": round(valid_rows / (B * L), 4), "ms_per_launch": round(kl_ms, 4), "timed_by": kl_how, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), **roof_extra}
 

@@ -100,12 +100,15 @@ class _LfdLossFn(torch.autograd.Function):
         phase0 = 0 | (L.LFD_PLANES_VALID if private_ws else 0)
         L.check(L.lib.fddm_lfd_backward(*args, phase0, dz_a.data_ptr(), dz_b.data_ptr(), st), "lfd_backward[0]")
         if group is not None:
-            # Only sum_b dz~*z~ crosses ranks, in fp32 (1/4 of the bytes of the fp64 block): the other moment,
-            # sum_b dz~, is identically zero over the GLOBAL batch because z~ has zero batch mean, so every
-            # rank's partial sum is rounding noise (~1e-8 of dz~) whether reduced or not.
-            m2 = bn.view(2, 2, T * D)[:, 1, :].float()
+            # Only sum_b dz~*z~ crosses ranks, in fp32 (1/4 of the bytes of the fp64 block).  The other moment,
+            # sum_b dz~ = sum_k (sum_b z~[b,t,k]) G[.,k] / N, is identically zero over the GLOBAL batch because
+            # z~ has zero global batch mean (a rank's partial sum is NOT zero), so it is set to zero instead
+            # of being reduced: the dropped term is rounding noise (~1e-7 relative).
+            v = bn.view(2, 2, T * D)
+            m2 = v[:, 1, :].float()
             torch.distributed.all_reduce(m2, op=torch.distributed.ReduceOp.SUM, group=group)
-            bn.view(2, 2, T * D)[:, 1, :].copy_(m2)
+            v[:, 1, :].copy_(m2)
+            v[:, 0, :].zero_()
         L.check(L.lib.fddm_lfd_backward(*args, 1, dz_a.data_ptr(), dz_b.data_ptr(), st), "lfd_backward[1]")
         return dz_a, dz_b, None
 

@@ -210,12 +210,20 @@ def _shard_worker(rank, world, port, q):
         loss = ((1 - dg) ** 2).sum() + 5e-3 * ((C - np.diag(dg)) ** 2).sum()
         G = 2 * 5e-3 * (C - np.diag(dg)); G[np.arange(D), np.arange(D)] = -2 * (1 - dg)
         dza = (bt.reshape(-1, D) @ G.T / N).reshape(a.shape); dzb = (at.reshape(-1, D) @ G / N).reshape(a.shape)
+        local_m1 = np.stack([dza.sum(0), dzb.sum(0)])
         bn = red(np.stack([dza.sum(0), (dza * at).sum(0), dzb.sum(0), (dzb * bt).sum(0)]))
         da = (dza - bn[0] / B - at * bn[1] / B) * rstd_a
         db = (dzb - bn[2] / B - bt * bn[3] / B) * rstd_b
         wl, wa, wb = O.lfd_loss(za, zb, 5e-3, dtype=np.float64, want_grad=True)
         assert abs(loss - wl) < 1e-10 * abs(wl)
         assert np.allclose(da, wa[sl], rtol=1e-8, atol=1e-14) and np.allclose(db, wb[sl], rtol=1e-8, atol=1e-14)
+        # what fddm_b200.losses does when sharded: only sum_b dz~*z~ is all-reduced; sum_b dz~ is zero over the
+        # GLOBAL batch (z~ has zero global batch mean) -- though not per rank -- and is replaced by 0
+        assert np.abs(bn[0]).max() < 1e-12 * np.abs(dza).max() and np.abs(bn[2]).max() < 1e-12 * np.abs(dzb).max()
+        assert np.abs(local_m1).max() > 1e-3 * np.abs(dza).max()          # a rank's partial sum is far from zero
+        da0 = (dza - at * bn[1] / B) * rstd_a
+        db0 = (dzb - bt * bn[3] / B) * rstd_b
+        assert np.allclose(da0, wa[sl], rtol=1e-8, atol=1e-14) and np.allclose(db0, wb[sl], rtol=1e-8, atol=1e-14)
 
         # Q10: delta is clipped by the GLOBAL min of t -> one MIN all-reduce of an int
         tmin = torch.tensor([int(t[sl].min())]); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)

@@ -32,12 +32,6 @@ int num_sms() {
   return cached[dev];
 }
 
-int max_smem_optin() {
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 227 * 1024;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 227 * 1024;
-  return n;
-}
 }  // namespace fddm
 
 extern "C" {

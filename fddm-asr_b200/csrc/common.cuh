@@ -24,7 +24,6 @@ namespace fddm {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
-int max_smem_optin();
 
 #define FDDM_CHECK_ARG(cond, ...)            \
   do {                                       \

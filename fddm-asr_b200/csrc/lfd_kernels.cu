@@ -418,10 +418,6 @@ __global__ void __launch_bounds__(256) lfd_bn_finalize_kernel(const T* __restric
   }
 }
 
-struct LfdArgs {
-  const void* za; const void* zb; int dtype; int64_t B, T, D;
-};
-
 int check_common(const char* what, const void* za, const void* zb, int dtype, int64_t B, int64_t T, int64_t D) {
   FDDM_CHECK_ARG(za && zb, "%s: null input", what);
   FDDM_CHECK_ARG(dtype_valid(dtype), "%s: bad dtype %d", what, dtype);

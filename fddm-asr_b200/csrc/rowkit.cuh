@@ -62,19 +62,6 @@ struct RegRow {
     const int nv = (nvec - tid + NT - 1) / NT;
     return (nv > 0 ? nv : 0) * N;
   }
-  // Unpredicated variants: visit ALL registers, including the padding lanes past the end of the row
-  // (they hold kNegInf after load_from_smem, i.e. exp() == 0).  Callers correct their sums by n_pad().
-  __device__ __forceinline__ int n_pad() const { return NT * EPT - nvec * N; }
-  template <class F>
-  __device__ __forceinline__ void for_all(F&& f) {
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) f(v[i]);
-  }
-  template <class F4, class F1>
-  __device__ __forceinline__ void for_all4(F4&& f4, F1&&) {
-#pragma unroll
-    for (int i = 0; i < EPT; i += 4) f4(&v[i]);
-  }
   // f4(x4) over groups of 4 consecutive valid elements (x4 points at 4 registers)
   template <class F4, class F1>
   __device__ __forceinline__ void for_each4(F4&& f4, F1&&) {
@@ -151,7 +138,6 @@ struct SmemRow {
     }
     for (int k = V4 + tid; k < V; k += NT) Vec16<T>::store1(dst + k, g(k, r[k]));
   }
-  __device__ __forceinline__ int n_pad() const { return 0; }
   __device__ __forceinline__ int owner_of(int k) const {
     const int V4 = V & ~3;
     return k < V4 ? (k >> 2) % NT : k - V4;
@@ -161,12 +147,6 @@ struct SmemRow {
     const int ng = (g - tid + NT - 1) / NT;
     return (ng > 0 ? ng : 0) * 4 + ((V4 + tid < V) ? 1 : 0);
   }
-  template <class F>
-  __device__ __forceinline__ void for_all(F&& f) {
-    for_each([&](int, float& x) { f(x); });
-  }
-  template <class F4, class F1>
-  __device__ __forceinline__ void for_all4(F4&& f4, F1&& f1) { for_each4(f4, f1); }
   // groups of 4 consecutive elements, then the (V % 4) tail one by one
   template <class F4, class F1>
   __device__ __forceinline__ void for_each4(F4&& f4, F1&& f1) {

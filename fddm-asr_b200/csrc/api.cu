@@ -2,12 +2,14 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fddm {
 namespace {
 thread_local char g_err[512] = "";
-thread_local int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs the backward launches on its own thread
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -17,7 +19,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms() {
   // per-device cache (the library is used by one process per GPU, but stay correct regardless)
@@ -37,5 +39,5 @@ int num_sms() {
 extern "C" {
 int fddm_version(void) { return FDDM_ABI_VERSION; }
 const char* fddm_last_error(void) { return fddm::g_err; }
-int64_t fddm_launch_count(void) { return fddm::g_launches; }
+int64_t fddm_launch_count(void) { return fddm::g_launches.load(std::memory_order_relaxed); }
 }

@@ -49,7 +49,7 @@ typedef enum {
 
 int fddm_version(void);
 const char* fddm_last_error(void);
-/* number of kernels launched by this library on the calling thread since load (bench evidence) */
+/* number of kernels launched by this library in this process since load (bench evidence) */
 int64_t fddm_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------

@@ -40,6 +40,55 @@ def test_library_exports_every_declared_symbol():
     assert set(fddm_b200._lib.SIGNATURES) == set(names)          # the ctypes table binds exactly the header
 
 
+def header_prototypes():
+    """name -> number of parameters, parsed from the C prototypes in include/fddm_b200.h"""
+    text = open(os.path.join(ROOT, "include", "fddm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(fddm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        out[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_ctypes_signatures_match_header_arity():
+    """A ctypes argtypes list that disagrees with the C prototype corrupts the call silently: the binding
+    table must have exactly as many parameters as each prototype, pointers where the header has pointers."""
+    import fddm_b200
+    protos = header_prototypes()
+    assert set(protos) == set(fddm_b200._lib.SIGNATURES)
+    for name, (_, argtypes) in fddm_b200._lib.SIGNATURES.items():
+        assert len(argtypes) == protos[name], f"{name}: header has {protos[name]} parameters, ctypes table {len(argtypes)}"
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fddm_b200.h")).read(), flags=re.S)
+    for m in re.finditer(r"\b(fddm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), [p.strip() for p in m.group(2).split(",")]
+        if params in ([""], ["void"]):
+            continue
+        argtypes = fddm_b200._lib.SIGNATURES[name][1]
+        for i, (prm, at) in enumerate(zip(params, argtypes)):
+            is_ptr = "*" in prm or "fddm_stream_t" in prm
+            assert is_ptr == (at is ctypes.c_void_p), f"{name} parameter {i} ({prm!r}) vs ctypes {at}"
+            if not is_ptr:
+                want = {"int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "int": ctypes.c_int, "float": ctypes.c_float,
+                        "double": ctypes.c_double}[prm.split()[0]]
+                assert at is want, f"{name} parameter {i} ({prm!r}) vs ctypes {at}"
+
+
+def test_dropin_shims_resolve_to_the_b200_implementation():
+    """fddm-asr_b200/dropin mirrors the reference's import paths."""
+    import importlib
+    import subprocess
+    import sys
+    code = ("from fddm.sched.diffusion_scheduler import DiscreteDiffusionScheduler as S;"
+            "from losses.fddm_losses import lfd_loss;"
+            "from sampler.jumpy_sampler import DiffusionJumpySampler, ModelAdapter;"
+            "print(S.__module__, lfd_loss.__module__, DiffusionJumpySampler.__module__, ModelAdapter.__module__)")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "fddm-asr_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["fddm_b200.scheduler", "fddm_b200.losses", "fddm_b200.sampler", "fddm_b200.sampler"]
+
+
 def test_host_only_entry_points():
     import fddm_b200
     lib = fddm_b200._lib.lib

@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from . import _lib as L
-from .scheduler import philox_seed_offset
+from .scheduler import multistep_coeffs, philox_seed_offset
 
 
 class ModelAdapter:
@@ -108,8 +108,12 @@ class DiffusionJumpySampler:
         if self.sampling_mode == "exact":
             flags |= L.JUMP_EXACT
             # Q2: t on the T_infer axis indexes the scheduler's (T_train-length) beta table as is
-            coeffs = self.scheduler.multistep_coeffs(t_tensor, int(delta))
-            eps = float(self.scheduler.eps)
+            # (works with any scheduler object that has a `betas` table, e.g. the reference's own class)
+            betas = getattr(self.scheduler, "betas", None)
+            if betas is None:
+                raise ValueError("scheduler must provide betas for sampling_mode='exact'")
+            coeffs = multistep_coeffs(t_tensor, int(delta), betas, int(getattr(self.scheduler, "K", self.K)))
+            eps = float(getattr(self.scheduler, "eps", 1e-8))
         else:
             abar_index = self._alpha_bar_index(max(0, t_scalar - delta))
             alpha_bar = self.alpha_bar if self.alpha_bar.device == dev else self.alpha_bar.to(dev)

@@ -75,14 +75,7 @@ class DiscreteDiffusionScheduler:
         the device without host synchronisation: fp32 [4B+1] = a_cum | b_cum | a_tgt | b_tgt | identity.
         `delta_cap`: optional int64 device scalar, the global-batch min of t when the batch is
         sharded over ranks (quirk Q10: the reference clips delta by t.min() over the whole batch)."""
-        t = t.to(self.device).long().contiguous()
-        L.require_cuda(t, self.betas)
-        B = t.numel()
-        coeffs = torch.empty(4 * B + 1, dtype=torch.float32, device=t.device)
-        L.check(L.lib.fddm_multistep_coeffs(t.data_ptr(), B, int(delta), L.ptr(delta_cap), self.betas.data_ptr(),
-                                            self.T, self.K, coeffs.data_ptr(), L.stream_ptr(t.device)),
-                "multistep_coeffs")
-        return coeffs
+        return multistep_coeffs(t.to(self.device), int(delta), self.betas, self.K, delta_cap=delta_cap)
 
     @torch.no_grad()
     def q_posterior_multi_step(self, xt_prob: torch.Tensor, x0hat_prob: torch.Tensor, t: torch.Tensor,
@@ -136,6 +129,21 @@ class DiscreteDiffusionScheduler:
                                         self.K, self.eps, L.ptr(exp_noise), seed, offset, L.ptr(philox_state),
                                         out.data_ptr(), L.stream_ptr(dev)), "sample_q_ids")
         return out
+
+
+@torch.no_grad()
+def multistep_coeffs(t: torch.Tensor, delta: int, betas: torch.Tensor, K: int, *,
+                     delta_cap: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fddm_multistep_coeffs for any scheduler object that exposes a `betas` table (sched:132-183)."""
+    t = t.long().contiguous()
+    betas = betas.to(device=t.device, dtype=torch.float32).contiguous()
+    L.require_cuda(t, betas)
+    B = t.numel()
+    coeffs = torch.empty(4 * B + 1, dtype=torch.float32, device=t.device)
+    L.check(L.lib.fddm_multistep_coeffs(t.data_ptr(), B, int(delta), L.ptr(delta_cap), betas.data_ptr(),
+                                        int(betas.numel()), int(K), coeffs.data_ptr(), L.stream_ptr(t.device)),
+            "multistep_coeffs")
+    return coeffs
 
 
 def philox_seed_offset(device: torch.device, generator: Optional[torch.Generator], increment: int):

@@ -43,6 +43,7 @@ WORKLOADS = {
     "c5shard": (64, 256, 8000, 768),
     "c2": (32, 128, 8000, 768),
     "c4": (64, 256, 32000, 768),
+    "c1": (8, 64, 4000, 256),          # BASELINE configs[0]: the reference's own CPU-sized case (used by the CPU tests)
 }
 T_TRAIN, T_INFER, R_JUMP, LAMBDA, TAU = 200, 20, 5, 5e-3, 1.0
 CPU_SLICE_B = 8            # batch slice the CPU arm runs per step (the path is linear in B)

@@ -76,7 +76,6 @@ def test_ctypes_signatures_match_header_arity():
 
 def test_dropin_shims_resolve_to_the_b200_implementation():
     """fddm-asr_b200/dropin mirrors the reference's import paths."""
-    import importlib
     import subprocess
     import sys
     code = ("from fddm.sched.diffusion_scheduler import DiscreteDiffusionScheduler as S;"

@@ -186,6 +186,49 @@ class ResidentDecoder:
         return self.logits
 
 
+def shard_check(fb, dev, group, world, rank, bn_allreduce="moment"):
+    """world>1 only: the batch-sharded kl_term / lfd_loss (values AND gradients, through the same host classes
+    the timed step uses) must equal this library's single-process evaluation of the whole batch (which the
+    -m gpu parity tests pin to the oracle).  Small batch; every rank builds the same global batch."""
+    dist = torch.distributed
+    Bg, L, V, D, T = 8 * world, 32, 4000, 256, 200
+    g = torch.Generator(device=dev).manual_seed(1)
+    logits = torch.randn(Bg, L, V, generator=g, device=dev) * 2
+    x0 = torch.randint(0, V, (Bg, L), generator=g, device=dev)
+    xt = torch.where(torch.rand(Bg, L, generator=g, device=dev) < 0.5, x0, torch.randint(0, V, (Bg, L), generator=g, device=dev))
+    t = torch.randint(1, T + 1, (Bg,), generator=g, device=dev)
+    mask = torch.rand(Bg, L, generator=g, device=dev) < 0.7
+    za = torch.randn(Bg, L, D, generator=g, device=dev)
+    zb = 0.8 * za + 0.6 * torch.randn(Bg, L, D, generator=g, device=dev)
+    sch = fb.DiscreteDiffusionScheduler(K=V, T=T, device=dev)
+    sl = slice(rank * Bg // world, (rank + 1) * Bg // world)
+    lg = logits.clone().requires_grad_(True); a = za.clone().requires_grad_(True); b = zb.clone().requires_grad_(True)
+    kl_ref = fb.SchedulerAdapter(sch).kl_term(xt, x0, lg, t, mask)
+    lf_ref = fb.lfd_loss(a, b, LAMBDA)
+    (kl_ref + 0.5 * lf_ref).backward()
+    lgs = logits[sl].clone().requires_grad_(True); a_s = za[sl].clone().requires_grad_(True); b_s = zb[sl].clone().requires_grad_(True)
+    kl = fb.SchedulerAdapter(sch, group=group).kl_term(xt[sl], x0[sl], lgs, t[sl], mask[sl])
+    op = fb.LfdPipeline(a_s, b_s, LAMBDA, group=group, bn_allreduce=bn_allreduce)
+    op.stats(); op.xcov()
+    lf = op.loss()
+    (kl + 0.5 * lf).backward()
+    part = fb.SchedulerAdapter(sch, group=group, defer_reduce=True).kl_term(xt[sl], x0[sl], logits[sl], t[sl], mask[sl]).detach().clone()
+    dist.all_reduce(part, group=group)
+    torch.cuda.synchronize(dev)
+
+    def rel(x, y):
+        return float((x.double() - y.double()).abs().max() / y.double().abs().max().clamp_min(1e-30))
+    errs = {"kl": abs(float(kl) - float(kl_ref)) / abs(float(kl_ref)), "lfd": abs(float(lf) - float(lf_ref)) / abs(float(lf_ref)),
+            "dlogits": rel(lgs.grad, lg.grad[sl]), "dza": rel(a_s.grad, a.grad[sl]), "dzb": rel(b_s.grad, b.grad[sl]),
+            "kl_deferred": abs(float(part) - float(kl_ref)) / abs(float(kl_ref))}
+    worst = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+    tol = 2e-5
+    out = {"ok": bool(float(worst) < tol), "tol": tol, "worst_over_ranks": float(worst), "bn_allreduce": bn_allreduce,
+           "global_batch": Bg, **{k: float(f"{v:.3e}") for k, v in errs.items()}}
+    return out
+
+
 def run_gpu(args):
     import fddm_b200 as fb
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -204,6 +247,15 @@ def run_gpu(args):
         group = dist.group.WORLD
     if args.gpus != world and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torchrun", file=sys.stderr)
+
+    shard = None
+    if world > 1:
+        shard = shard_check(fb, dev, group, world, rank)
+        if not shard["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "shard_check failed: the batch-sharded path disagrees with the whole-batch "
+                                           "evaluation", "shard_check": shard, "n_gpus": world}), flush=True)
+            teardown(world, dev, code=3)
 
     B, L, V, D = WORKLOADS[args.workload]
     dtype = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[args.dtype]
@@ -421,10 +473,41 @@ def run_gpu(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "loss": float(total.detach()),
+            "shard_check": shard,
         }
-        print(json.dumps(line))
-    if world > 1:
+        print(json.dumps(line), flush=True)
+    # the captured graph holds NCCL kernels (a reference on the communicator): it must die before the group does
+    graph = g_total = g_xnew = total = x_new = None
+    ext_ev.clear(); kl_ev.clear()
+    teardown(world, dev)
+
+
+def teardown(world, dev, code=0):
+    """Leave the process without hanging.  Round-1 incident: every multi-rank run hung at
+    exit once the step was a CUDA graph, because destroy_process_group() was called while the captured graph --
+    which holds NCCL kernels and so a reference on the communicator -- was still alive.  Order here: the JSON
+    line is already printed and flushed; drop the graph and everything captured with it, synchronise, barrier,
+    then destroy the group under a watchdog, and finally _exit so that no destructor can block either."""
+    import gc
+    import threading
+    sys.stdout.flush(); sys.stderr.flush()
+    if world <= 1:
+        if code:
+            sys.exit(code)
+        return
+    wd = threading.Timer(45.0, lambda: os._exit(code))            # the result is out: never hold the GPUs hostage
+    wd.daemon = True
+    wd.start()
+    gc.collect()
+    torch.cuda.synchronize(dev)
+    try:
+        torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
         torch.distributed.destroy_process_group()
+    except Exception as e:                                      # pragma: no cover
+        print(f"bench.py: teardown: {type(e).__name__}: {e}", file=sys.stderr)
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(code)
 
 
 def run_reference(args):

@@ -278,187 +278,6 @@ umma_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA_hi,
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (compiled, selected only with FDDM_UMMA_PERSISTENT=1; not yet run on hardware -- the
-// round-1 GPU budget was exhausted when it was written): persistent variant.  grid = min(work, SMs);
-// every CTA walks work items w = blockIdx.x, += gridDim.x with the same (tile, split) decomposition, the
-// operand ring runs on across work items, and TWO 256-column TMEM accumulators alternate so the
-// epilogue of item i (TMEM -> global, 131 KB) overlaps the main loop of item i+1.  ncu of the
-// one-tile-per-CTA kernel: tensor pipe 25 % busy on the backward contraction (prologue + epilogue
-// exposed around a 24-k-block main loop, 2.6 waves).
-// ------------------------------------------------------------------------------------------------
-template <int TERMS>
-__global__ void __launch_bounds__(kThreads, 1)
-umma_gemm_persistent_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA_hi,
-                            const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
-                            const __grid_constant__ CUtensorMap tmB_lo, const int total_work) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_acc_full[2], s_acc_empty[2];
-  __shared__ uint32_t s_tmem_base;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t stage_bytes = TERMS * (kTileA + kTileB);
-  const int tiles = p.tiles_m * p.tiles_n;
-
-  if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_acc_full[b], 1);
-      mbar_init(&s_acc_empty[b], kEpiWarps);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                 "r"(static_cast<uint32_t>(2 * kTmemCols))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = s_tmem_base;
-
-  // decomposition of a work item (same as the one-tile-per-CTA kernel's blockIdx mapping)
-  auto item = [&](int w, int64_t& m0, int64_t& n0, int64_t& k_begin, int& num_kb, int& split) {
-    split = w / tiles;
-    const int tile = w % tiles;
-    m0 = static_cast<int64_t>(tile / p.tiles_n) * kBM;
-    n0 = static_cast<int64_t>(tile % p.tiles_n) * p.BN;
-    k_begin = static_cast<int64_t>(split) * p.k_per_split;
-    const int64_t k_end = min(static_cast<int64_t>(p.K), k_begin + p.k_per_split);
-    num_kb = static_cast<int>((k_end - k_begin + kBK - 1) / kBK);
-  };
-
-  if (warp == 0) {
-    // ===== producer =====
-    const uint32_t bytesA = kBM * kBK * 2, bytesB = static_cast<uint32_t>(p.BN) * kBK * 2;
-    const uint32_t tx = TERMS * (bytesA + bytesB);
-    uint32_t it = 0;                                   // k-blocks issued by this CTA so far (ring position)
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      int64_t m0, n0, k_begin; int num_kb, split;
-      item(w, m0, n0, k_begin, num_kb, split);
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = static_cast<int>(it % p.stages);
-        const uint32_t round = it / p.stages;
-        if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1);
-        if (lane == 0) mbar_arrive_expect_tx(&s_full[s], tx);
-        __syncwarp();
-        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-        const int64_t k0 = k_begin + static_cast<int64_t>(kb) * kBK;
-        const TilePlan ta = plan_tile(p.A, m0, kBM, k0), tb = plan_tile(p.B, n0, p.BN, k0);
-#pragma unroll
-        for (int term = 0; term < TERMS; ++term) {
-          const __nv_bfloat16* pa = term == 0 ? p.A.hi : p.A.lo;
-          const __nv_bfloat16* pb = term == 0 ? p.B.hi : p.B.lo;
-          uint8_t* da = st + term * kTileA;
-          uint8_t* db = st + TERMS * kTileA + term * kTileB;
-          if (p.A.mn_is_col) {
-            if (lane == 0) tma_load_2d(da, term == 0 ? &tmA_hi : &tmA_lo, static_cast<int>(k0 * 8), static_cast<int>(m0 / 8), &s_full[s]);
-          } else {
-            for (int c = lane; c < ta.ncopies; c += 32)
-              tma_load_1d(da + static_cast<size_t>(c) * ta.bytes, pa + ta.src_base + c * ta.src_stride, ta.bytes, &s_full[s]);
-          }
-          if (p.B.mn_is_col) {
-            if (lane == 1) tma_load_2d(db, term == 0 ? &tmB_hi : &tmB_lo, static_cast<int>(k0 * 8), static_cast<int>(n0 / 8), &s_full[s]);
-          } else {
-            for (int c = lane; c < tb.ncopies; c += 32)
-              tma_load_1d(db + static_cast<size_t>(c) * tb.bytes, pb + tb.src_base + c * tb.src_stride, tb.bytes, &s_full[s]);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(p.A.mn_is_col, p.B.mn_is_col, p.BN);
-      const uint32_t csA = p.A.mn_is_col ? kBK * 16u : kBM * 16u;
-      const uint32_t csB = p.B.mn_is_col ? kBK * 16u : static_cast<uint32_t>(p.BN) * 16u;
-      const uint32_t lboA = p.A.mn_is_col ? 128u : csA, sboA = p.A.mn_is_col ? csA : 128u;
-      const uint32_t lboB = p.B.mn_is_col ? 128u : csB, sboB = p.B.mn_is_col ? csB : 128u;
-      const uint32_t advA = p.A.mn_is_col ? 256u : 2u * csA;
-      const uint32_t advB = p.B.mn_is_col ? 256u : 2u * csB;
-      uint32_t it = 0, local = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
-        int64_t m0, n0, k_begin; int num_kb, split;
-        item(w, m0, n0, k_begin, num_kb, split);
-        const uint32_t buf = local & 1, use = local >> 1;
-        if (use > 0) {                               // the epilogue must have drained this accumulator
-          mbar_wait(&s_acc_empty[buf], (use - 1) & 1);
-          tc_fence_after();
-        }
-        const uint32_t tmem_d = tmem_base + buf * kTmemCols;
-        uint32_t accum = 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = static_cast<int>(it % p.stages);
-          const uint32_t round = it / p.stages;
-          mbar_wait(&s_full[s], round & 1);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-          const uint32_t a_hi = st, a_lo = st + kTileA, b_hi = st + TERMS * kTileA, b_lo = b_hi + kTileB;
-#pragma unroll
-          for (int term = 0; term < (TERMS == 2 ? 3 : 1); ++term) {
-            const uint32_t a_base = (term == 2) ? a_lo : a_hi;
-            const uint32_t b_base = (term == 1) ? b_lo : b_hi;
-#pragma unroll
-            for (int ks = 0; ks < kBK / 16; ++ks) {
-              umma_bf16(tmem_d, make_smem_desc(a_base + ks * advA, lboA, sboA),
-                        make_smem_desc(b_base + ks * advB, lboB, sboB), idesc, accum);
-              accum = 1;
-            }
-          }
-          umma_commit(&s_empty[s]);
-        }
-        umma_commit(&s_acc_full[buf]);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===== epilogue =====
-    const int q = warp & 3;
-    uint32_t local = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
-      int64_t m0, n0, k_begin; int num_kb, split;
-      item(w, m0, n0, k_begin, num_kb, split);
-      const uint32_t buf = local & 1, use = local >> 1;
-      mbar_wait(&s_acc_full[buf], use & 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * kTmemCols;
-      const int64_t m = m0 + q * 32 + lane;
-      float* orow = p.out + static_cast<int64_t>(split) * p.out_split_stride + m * p.out_ld;
-      for (int c = 0; c < p.BN; c += 16) {
-        float v[16];
-        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
-        const int64_t n = n0 + c;
-        if (m < p.M && n < p.N) {
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            if (n + 4 * h < p.N) {
-              float4 o = make_float4(v[4 * h] * p.alpha, v[4 * h + 1] * p.alpha, v[4 * h + 2] * p.alpha,
-                                     v[4 * h + 3] * p.alpha);
-              *reinterpret_cast<float4*>(orow + n + 4 * h) = o;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_acc_empty[buf]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(2 * kTmemCols))
-                 : "memory");
-  }
-}
-
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -549,26 +368,6 @@ int umma_gemm(const PackedOperand& A, const PackedOperand& B, int64_t M, int64_t
   if (B.mn_is_col) {
     if (int rc = make_plane_map(&tm[2], B.hi, B.R_pad, B.C_pad, p.BN)) return rc;
     if (terms == 2) if (int rc = make_plane_map(&tm[3], B.lo, B.R_pad, B.C_pad, p.BN)) return rc;
-  }
-  static const bool persistent = [] {
-    const char* e = getenv("FDDM_UMMA_PERSISTENT");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (persistent) {                                 // EXPERIMENTAL, see umma_gemm_persistent_kernel
-    const int pgrid = static_cast<int>(std::min<int64_t>(grid, num_sms()));
-    if (terms == 2) {
-      FDDM_CUDA_OK(cudaFuncSetAttribute(umma_gemm_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-      umma_gemm_persistent_kernel<2><<<pgrid, kThreads, smem, stream>>>(p, tm[0], tm[1], tm[2], tm[3],
-                                                                        static_cast<int>(grid));
-    } else {
-      FDDM_CUDA_OK(cudaFuncSetAttribute(umma_gemm_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-      umma_gemm_persistent_kernel<1><<<pgrid, kThreads, smem, stream>>>(p, tm[0], tm[1], tm[2], tm[3],
-                                                                        static_cast<int>(grid));
-    }
-    FDDM_LAUNCH_OK();
-    return FDDM_OK;
   }
   if (terms == 2) {
     FDDM_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -238,6 +238,10 @@ int jump_launch_f16(const JumpParams& p, int noise, cudaStream_t stream);
 #ifdef FDDM_JUMP_DT
 namespace {
 
+// counter-domain tag of the jump kernels (xor-ed into counter word 3) so that a jump and a sample_q
+// call sharing one {seed, offset} never evaluate Philox on the same counter
+constexpr uint32_t kJumpDomain = 0x4A554D50u;
+
 struct JumpRowCtx {
   int xt;
   float a_c, b_c, a_g, b_g;  // exact
@@ -598,6 +602,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     if (NOISE == 2) {
       NoisePhilox nz;
       philox_key_off(p.philox_state, p.key, p.off, nz.key, nz.off); nz.row = static_cast<uint32_t>(mt.row);
+      nz.off.y ^= kJumpDomain;
       id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
@@ -636,6 +641,7 @@ __global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpPara
     if (NOISE == 2) {
       NoisePhilox nz;
       philox_key_off(p.philox_state, p.key, p.off, nz.key, nz.off); nz.row = static_cast<uint32_t>(r);
+      nz.off.y ^= kJumpDomain;
       id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;

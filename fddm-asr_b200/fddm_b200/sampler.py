@@ -57,7 +57,8 @@ class DiffusionJumpySampler:
         self.noise_fn = None
         self.generator: Optional[torch.Generator] = None
         # optional int64[2] device tensor {seed, offset} read by the kernel instead of the host-side
-        # generator state (the caller advances the offset): makes a jump replayable in a CUDA graph
+        # generator state; every sampling jump advances the offset on the device (a captured add), which
+        # makes a jump -- or a whole chain -- replayable in a CUDA graph with fresh noise per replay
         self.philox_state: Optional[torch.Tensor] = None
 
     # sampler:219-236, including the 0-based table indexed by a 1-based train-axis index (Q3)
@@ -143,6 +144,10 @@ class DiffusionJumpySampler:
                                      offset, L.ptr(self.philox_state if (sample and noise is None) else None),
                                      ws.data_ptr(), x_out.data_ptr(), L.ptr(amax), L.ptr(p_x0),
                                      L.stream_ptr(dev)), "jump_step")
+        if sample and noise is None and self.philox_state is not None:
+            # stream-ordered (and graph-capturable) advance of the device-side offset: the next jump of the
+            # chain -- and the next replay of a captured chain -- draws fresh variates
+            self.philox_state[1:].add_(4)
         return x_out, p_x0, amax
 
     @torch.no_grad()

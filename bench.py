@@ -220,7 +220,7 @@ def shard_check(fb, dev, group, world, rank, bn_allreduce="moment"):
         return float((x.double() - y.double()).abs().max() / y.double().abs().max().clamp_min(1e-30))
     errs = {"kl": abs(float(kl.detach()) - float(kl_ref.detach())) / abs(float(kl_ref.detach())), "lfd": abs(float(lf.detach()) - float(lf_ref.detach())) / abs(float(lf_ref.detach())),
             "dlogits": rel(lgs.grad, lg.grad[sl]), "dza": rel(a_s.grad, a.grad[sl]), "dzb": rel(b_s.grad, b.grad[sl]),
-            "kl_deferred": abs(float(part) - float(kl_ref)) / abs(float(kl_ref.detach()))}
+            "kl_deferred": abs(float(part) - float(kl_ref.detach())) / abs(float(kl_ref.detach()))}
     worst = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
     tol = 2e-5

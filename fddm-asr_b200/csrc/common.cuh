@@ -52,6 +52,25 @@ int num_sms();
     ::fddm::count_launch();                                                            \
   } while (0)
 
+// NVTX range around every extern "C" entry point (visible in nsys / ncu timelines; a no-op costing one
+// predictable branch when no tool is attached).
+struct ApiRange {
+  explicit ApiRange(const char* name);
+  ~ApiRange();
+};
+#define FDDM_API_RANGE() ::fddm::ApiRange _fddm_api_range_(__func__)
+
+// Declared right before a kernel launch: an NVTX range named after the kernel and, while
+// fddm_profile_enable(1) is in effect (bench.py's per-kernel roofline pass), a pair of CUDA events on the
+// launching stream bracketing exactly that launch.  Nothing is recorded while the stream is being captured.
+struct KernelScope {
+  KernelScope(const char* name, cudaStream_t stream);
+  ~KernelScope();
+  const char* name_;
+  cudaStream_t stream_;
+  cudaEvent_t e0_;
+};
+
 static inline size_t dtype_size(int dtype) { return dtype == FDDM_F32 ? 4 : 2; }
 static inline bool dtype_valid(int dtype) { return dtype == FDDM_F32 || dtype == FDDM_BF16 || dtype == FDDM_F16; }
 

@@ -202,6 +202,7 @@ extern "C" {
 
 int fddm_q_sample_dense(const float* x0_prob, const int64_t* t, const float* alpha_bar, int64_t T, int64_t B, int64_t L,
                         int64_t K, float eps, float* out, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(x0_prob && t && alpha_bar && out, "q_sample_dense: null pointer argument");
@@ -210,6 +211,7 @@ int fddm_q_sample_dense(const float* x0_prob, const int64_t* t, const float* alp
   const int rows = static_cast<int>(B * L);
   const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(num_sms()) * 8));
   const float u = static_cast<float>(1.0 / static_cast<double>(K));
+  KernelScope ks("q_sample_dense_kernel", stream);
   if (K <= kNT * kEPT)
     q_sample_dense_kernel<true><<<grid, kNT, 0, stream>>>(x0_prob, t, alpha_bar, static_cast<int>(T),
                                                           static_cast<int>(L), static_cast<int>(K), rows, eps, u, out);
@@ -222,6 +224,7 @@ int fddm_q_sample_dense(const float* x0_prob, const int64_t* t, const float* alp
 
 int fddm_q_posterior_dense(const float* xt_prob, const float* x0hat_prob, const int64_t* t, const float* betas,
                            int64_t T, int64_t B, int64_t L, int64_t K, float eps, float* out, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(xt_prob && x0hat_prob && t && betas && out, "q_posterior_dense: null pointer argument");
@@ -229,6 +232,7 @@ int fddm_q_posterior_dense(const float* xt_prob, const float* x0hat_prob, const 
   FDDM_CHECK_ARG(B * L < (1ll << 31) && K < (1ll << 30), "q_posterior_dense: size too large");
   const int rows = static_cast<int>(B * L);
   const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(num_sms()) * 4));
+  KernelScope ks("q_posterior_dense_kernel", stream);
   if (K <= kNT * kEPT)
     q_posterior_dense_kernel<false, true><<<grid, kNT, 0, stream>>>(xt_prob, x0hat_prob, t, betas, nullptr,
                                                                     static_cast<int>(T), static_cast<int>(B),
@@ -245,10 +249,12 @@ int fddm_q_posterior_dense(const float* xt_prob, const float* x0hat_prob, const 
 
 int fddm_multistep_coeffs(const int64_t* t, int64_t B, int64_t delta, const int64_t* delta_cap, const float* betas,
                           int64_t T, int64_t K, float* coeffs, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(t && betas && coeffs, "multistep_coeffs: null pointer argument");
   FDDM_CHECK_ARG(B > 0 && K > 0 && T > 0 && B < (1ll << 30), "multistep_coeffs: bad size");
+  KernelScope ks("multistep_coeffs_kernel", stream);
   multistep_coeffs_kernel<<<1, 256, 0, stream>>>(t, static_cast<int>(B), static_cast<long long>(delta), delta_cap, betas,
                                                  static_cast<int>(T), static_cast<int>(K), coeffs);
   FDDM_LAUNCH_OK();
@@ -257,6 +263,7 @@ int fddm_multistep_coeffs(const int64_t* t, int64_t B, int64_t delta, const int6
 
 int fddm_q_posterior_multi_dense(const float* xt_prob, const float* x0hat_prob, const float* coeffs, int64_t B,
                                  int64_t L, int64_t K, float eps, float* out, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(xt_prob && x0hat_prob && coeffs && out, "q_posterior_multi_dense: null pointer argument");
@@ -264,6 +271,7 @@ int fddm_q_posterior_multi_dense(const float* xt_prob, const float* x0hat_prob, 
   FDDM_CHECK_ARG(B * L < (1ll << 31) && K < (1ll << 30), "q_posterior_multi_dense: size too large");
   const int rows = static_cast<int>(B * L);
   const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(num_sms()) * 4));
+  KernelScope ks("q_posterior_multi_dense_kernel", stream);
   if (K <= kNT * kEPT)
     q_posterior_dense_kernel<true, true><<<grid, kNT, 0, stream>>>(xt_prob, x0hat_prob, nullptr, nullptr, coeffs, 0,
                                                                    static_cast<int>(B), static_cast<int>(L),

@@ -437,6 +437,7 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
   const bool aligned = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
                        (!BWD || reinterpret_cast<uintptr_t>(p.grad) % 16 == 0);
   const int sms = num_sms();
+  KernelScope ks(BWD ? "kl_rows_fwdbwd" : "kl_rows_fwd", stream);
   if (aligned && p.V <= 32768) {
     int nt, ept;
     if (p.V <= 4096) { nt = 128; ept = 32; }
@@ -514,6 +515,7 @@ size_t fddm_kl_workspace_bytes(int64_t B, int64_t L) {
 int fddm_kl_forward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
                     const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
                     double batch_div, void* workspace, float* loss_out, fddm_stream_t stream) {
+  FDDM_API_RANGE();
   return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, betas, T, B, L, V, batch_div, nullptr, workspace, loss_out,
                         nullptr, false, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -522,11 +524,13 @@ int fddm_kl_forward_backward(const void* logits, int dtype, const int64_t* xt, c
                              const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
                              double batch_div, const float* grad_scale, void* workspace, float* loss_out,
                              void* grad_logits, fddm_stream_t stream) {
+  FDDM_API_RANGE();
   return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, betas, T, B, L, V, batch_div, grad_scale, workspace,
                         loss_out, grad_logits, true, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fddm_scale_inplace(void* x, int dtype, int64_t n, const float* num, const float* den, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(x && num, "scale_inplace: null pointer");
@@ -535,6 +539,7 @@ int fddm_scale_inplace(void* x, int dtype, int64_t n, const float* num, const fl
   FDDM_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0, "scale_inplace: x must be 16-byte aligned");
   if (n == 0) return FDDM_OK;
   const int grid = num_sms() * 8;
+  KernelScope ks("scale_inplace_kernel", stream);
   if (dtype == FDDM_F32) {
     scale_inplace_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(x), n / 4, n, num, den);
   } else if (dtype == FDDM_BF16) {

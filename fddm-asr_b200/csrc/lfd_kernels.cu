@@ -441,6 +441,7 @@ int pick_bsplit(int64_t nthreads_plane, int64_t B) {
 
 int launch_tables(const double* sums, int64_t TD, double n_batch, float eps, float* tables, cudaStream_t stream) {
   const int64_t n = 2 * TD;
+  KernelScope ks("lfd_tables_kernel", stream);
   lfd_tables_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(sums, TD, n_batch, eps, tables);
   FDDM_LAUNCH_OK();
   return FDDM_OK;
@@ -452,6 +453,7 @@ int launch_stats(const void* za, const void* zb, int dtype, int64_t B, int64_t T
   const int n = vec ? Vec16<T>::N : 1;
   const int64_t nthr = (TD + n - 1) / n;
   const int bsplit = pick_bsplit(nthr, B);
+  KernelScope ks("lfd_stats_kernel", stream);
   if (bsplit > 1) FDDM_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * TD, stream));
   dim3 grid(static_cast<unsigned>((nthr + 255) / 256), 2, bsplit);
   if (vec)
@@ -471,6 +473,7 @@ int launch_bn(const void* za, const void* zb, int dtype, int64_t B, int64_t TD, 
   const int n = vec ? Vec16<T>::N : 1;
   const int64_t nthr = (TD + n - 1) / n;
   const int bsplit = pick_bsplit(nthr, B);
+  KernelScope ks("lfd_bn_reduce_kernel", stream);
   if (bsplit > 1) FDDM_CUDA_OK(cudaMemsetAsync(bn, 0, sizeof(double) * 4 * TD, stream));
   dim3 grid(static_cast<unsigned>((nthr + 255) / 256), 2, bsplit);
   if (vec)
@@ -493,6 +496,7 @@ int launch_finalize(const void* za, const void* zb, int dtype, int64_t B, int64_
   const int64_t nthr = (TD + n - 1) / n;
   const int bsplit = pick_bsplit(nthr, B);
   dim3 grid(static_cast<unsigned>((nthr + 255) / 256), 2, bsplit);
+  KernelScope ks("lfd_bn_finalize_kernel", stream);
   if (vec)
     lfd_bn_finalize_kernel<T, true><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb), dza,
                                                               dzb, tables, bn, inv_nb, grad_scale, static_cast<int>(B),
@@ -544,6 +548,7 @@ int standardise_and_pack(const void* z_a, const void* z_b, int dtype, int64_t B,
   __nv_bfloat16 *a_hi = pl, *a_lo = terms == 2 ? pl + pe : nullptr, *b_hi = pl + 2 * pe,
                 *b_lo = terms == 2 ? pl + 3 * pe : nullptr;
   dim3 grid(static_cast<unsigned>(Dp / 64), static_cast<unsigned>(Rp / 256));
+  KernelScope ks("lfd_pack_kernel", stream);
   if (dtype == FDDM_F32)
     lfd_pack_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(z_a), static_cast<const float*>(z_b),
                                                      tables, rows, static_cast<int>(T), static_cast<int>(D), Rp, a_hi,
@@ -584,6 +589,7 @@ size_t fddm_lfd_workspace_bytes(int64_t B, int64_t T, int64_t D) {
 
 int fddm_lfd_stats(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D, double* sums,
                    fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_common("lfd_stats", z_a, z_b, dtype, B, T, D)) return rc;
@@ -593,6 +599,7 @@ int fddm_lfd_stats(const void* z_a, const void* z_b, int dtype, int64_t B, int64
 
 int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D, const double* sums,
                   double n_batch_global, float eps, void* workspace, float* cov, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_common("lfd_xcov", z_a, z_b, dtype, B, T, D)) return rc;
@@ -612,6 +619,7 @@ int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_
   const int splits = pick_splits(tiles, rows);
   if (int rc = umma_gemm(A, Bo, D, D, rows, splits, terms, 1.0f, partial, D, D * D, stream)) return rc;
   const int64_t n = D * D;
+  KernelScope ks("lfd_splitk_reduce_kernel", stream);
   lfd_splitk_reduce_kernel<<<static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, num_sms() * 8)), 256, 0,
                              stream>>>(partial, splits, n, static_cast<int>(D),
                                        reinterpret_cast<const double*>(ws + lay.off_diag), cov);
@@ -621,6 +629,7 @@ int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_
 
 int fddm_lfd_loss(const float* cov, int64_t D, double n_rows_global, float lambda_offdiag, void* workspace,
                   float* loss_out, float* G, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(cov && workspace && loss_out && G, "lfd_loss: null pointer argument");
@@ -628,6 +637,7 @@ int fddm_lfd_loss(const float* cov, int64_t D, double n_rows_global, float lambd
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const int grid = static_cast<int>(std::min<int64_t>((D * D + 255) / 256, std::min<int64_t>(num_sms() * 4,
                                                                               LfdWorkspace::kMaxPartials)));
+  KernelScope ks("lfd_loss_kernel", stream);
   lfd_loss_kernel<<<grid, 256, 0, stream>>>(cov, static_cast<int>(D), 1.0 / n_rows_global, lambda_offdiag,
                                             reinterpret_cast<unsigned int*>(ws),
                                             reinterpret_cast<double*>(ws + LfdWorkspace::kCounters), loss_out, G);
@@ -638,6 +648,7 @@ int fddm_lfd_loss(const float* cov, int64_t D, double n_rows_global, float lambd
 int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D, const double* sums,
                       double n_batch_global, float eps, const float* G, double n_rows_global, const float* grad_scale,
                       void* workspace, double* bn_sums, int phase, void* dz_a, void* dz_b, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_common("lfd_backward", z_a, z_b, dtype, B, T, D)) return rc;
@@ -662,9 +673,12 @@ int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, in
     const int64_t Dp = pack_pad(D);
     __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_gpack);
     const size_t ge = lay.gplane_bytes / 2;
-    lfd_pack_g_kernel<<<dim3(static_cast<unsigned>(Dp / 8), static_cast<unsigned>(Dp / 256)), 256, 0, stream>>>(
-        G, static_cast<int>(D), Dp, gp, gp + ge, gp + 2 * ge, gp + 3 * ge);
-    FDDM_LAUNCH_OK();
+    {
+      KernelScope ks("lfd_pack_g_kernel", stream);
+      lfd_pack_g_kernel<<<dim3(static_cast<unsigned>(Dp / 8), static_cast<unsigned>(Dp / 256)), 256, 0, stream>>>(
+          G, static_cast<int>(D), Dp, gp, gp + ge, gp + 2 * ge, gp + 3 * ge);
+      FDDM_LAUNCH_OK();
+    }
     const float alpha = static_cast<float>(1.0 / n_rows_global);
     PackedOperand Za{}, Zb{}, Gk{}, Gt{};
     planes_of(ws, lay, B, T, D, 2, 0, Za, Zb);

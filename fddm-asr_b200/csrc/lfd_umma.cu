@@ -369,6 +369,7 @@ int umma_gemm(const PackedOperand& A, const PackedOperand& B, int64_t M, int64_t
     if (int rc = make_plane_map(&tm[2], B.hi, B.R_pad, B.C_pad, p.BN)) return rc;
     if (terms == 2) if (int rc = make_plane_map(&tm[3], B.lo, B.R_pad, B.C_pad, p.BN)) return rc;
   }
+  KernelScope ks(A.mn_is_col ? "umma_gemm_fwd (z~^T z~, split-K)" : "umma_gemm_bwd (z~ G)", stream);
   if (terms == 2) {
     FDDM_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));

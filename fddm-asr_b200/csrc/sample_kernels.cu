@@ -665,6 +665,7 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
                  (!(p.flags & FDDM_JUMP_WRITE_P) || reinterpret_cast<uintptr_t>(p.p_out) % 16 == 0);
   if (NOISE == 1) aligned = aligned && (noise_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
   const int sms = num_sms();
+  KernelScope ks(NOISE == 0 ? "jump_rows_greedy" : (NOISE == 1 ? "jump_rows_injected_noise" : "jump_rows_philox"), stream);
   if (aligned && p.K <= 32768 && p.work != nullptr) {
     int nt, ept;
     if (p.K <= 4096) { nt = 128; ept = 32; }
@@ -727,6 +728,7 @@ extern "C" {
 int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_bar, int64_t T, int64_t B, int64_t L,
                       int64_t K, float eps, const float* exp_noise, uint64_t seed, uint64_t offset,
                       const uint64_t* philox_state, int64_t* xt_out, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(x0 && t && alpha_bar && xt_out, "sample_q_ids: null pointer argument");
@@ -741,6 +743,7 @@ int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_ba
   p.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   p.off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
   p.philox_state = philox_state;
+  KernelScope ks(exp_noise ? "sample_q_kernel" : "sample_q_closed_kernel", stream);
   if (exp_noise) {
     const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(num_sms()) * 8));
     sample_q_kernel<256, false><<<grid, 256, 0, stream>>>(p);
@@ -755,6 +758,7 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
                    int64_t abar_index, int64_t B, int64_t L, int64_t K, int flags, float temperature, float eps,
                    const float* exp_noise, uint64_t seed, uint64_t offset, const uint64_t* philox_state,
                    void* workspace, int64_t* x_out, int64_t* argmax_p_out, void* p_x0_out, fddm_stream_t stream_) {
+  FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FDDM_CHECK_ARG(logits && x_t && x_out, "jump_step: null pointer argument");

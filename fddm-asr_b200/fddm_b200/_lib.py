@@ -41,6 +41,8 @@ SIGNATURES = {
     "fddm_version": (_i32, []),
     "fddm_last_error": (C.c_char_p, []),
     "fddm_launch_count": (_i64, []),
+    "fddm_profile_enable": (_i32, [_i32]),
+    "fddm_profile_read": (_i64, [_vp, _i64]),
     "fddm_q_sample_dense": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp]),
     "fddm_sample_q_ids": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _u64, _u64, _vp, _vp, _vp]),
     "fddm_q_posterior_dense": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp]),
@@ -117,6 +119,23 @@ def stream_ptr(device: torch.device) -> int:
 
 def launch_count() -> int:
     return int(lib.fddm_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    """Per-kernel CUDA-event timing inside the library (measurement aid, see include/fddm_b200.h)."""
+    lib.fddm_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """{kernel name: (launches, total milliseconds)} of the launches recorded since profile_enable(True)."""
+    need = int(lib.fddm_profile_read(None, 0))
+    buf = C.create_string_buffer(need + 16)
+    lib.fddm_profile_read(C.cast(buf, C.c_void_p), need + 16)
+    out = {}
+    for line in buf.value.decode("utf-8", "replace").splitlines():
+        name, n, ms = line.split("\t")
+        out[name] = (int(n), float(ms))
+    return out
 
 
 _zero_ws = {}

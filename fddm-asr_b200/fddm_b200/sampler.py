@@ -151,13 +151,20 @@ class DiffusionJumpySampler:
         return x_out, p_x0, amax
 
     @torch.no_grad()
-    def sample(self, cond_c: Tensor, seq_len: int, init: Literal["uniform", "random"] = "uniform"
-               ) -> Tuple[Tensor, Tensor]:
-        """sampler:241-293.  Returns (x_0 ids [B,L], p_x0_last [B,L,K])."""
+    def sample(self, cond_c: Tensor, seq_len: int, init: Literal["uniform", "random"] = "uniform", *,
+               x_init: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """sampler:241-293.  Returns (x_0 ids [B,L], p_x0_last [B,L,K]).
+        `x_init` (extra, keyword-only): the initial ids x_T instead of drawing them here (parity tests,
+        CUDA-graph replay with caller-owned state)."""
         B = cond_c.size(0)
         device = cond_c.device
-        # both `init` values draw uniform random ids in the reference (Q8, sampler:276-280)
-        x_t_idx = torch.randint(low=0, high=self.K, size=(B, seq_len), device=device, generator=self.generator)
+        if x_init is not None:
+            if tuple(x_init.shape) != (B, seq_len):
+                raise ValueError(f"x_init must have shape ({B}, {seq_len})")
+            x_t_idx = x_init.long()
+        else:
+            # both `init` values draw uniform random ids in the reference (Q8, sampler:276-280)
+            x_t_idx = torch.randint(low=0, high=self.K, size=(B, seq_len), device=device, generator=self.generator)
         t = self.T_infer
         p_x0_last = None
         x_0_idx = None

@@ -40,7 +40,7 @@ typedef enum {
 } fddm_status_t;
 
 #define FDDM_MAX_VOCAB 49152       /* one fp32 row must fit the 227 KB shared memory of an SM */
-#define FDDM_ABI_VERSION 2
+#define FDDM_ABI_VERSION 3
 
 /* jump_step flags */
 #define FDDM_JUMP_EXACT   0x1      /* sampling_mode == "exact" (else "fast"), sampler:192-209 */
@@ -51,6 +51,14 @@ int fddm_version(void);
 const char* fddm_last_error(void);
 /* number of kernels launched by this library in this process since load (bench evidence) */
 int64_t fddm_launch_count(void);
+
+/* Measurement aid (bench.py's per-kernel roofline block).  While enabled, every kernel launch of the
+ * library is bracketed by a pair of CUDA events on its stream (never during stream capture); every entry
+ * point and launch is also an NVTX range, always.  fddm_profile_enable(1) clears earlier records.
+ * fddm_profile_read synchronises the recorded events and writes "kernel<TAB>launches<TAB>total_ms" lines
+ * into buf (NUL-terminated) when cap suffices; returns the bytes needed. */
+int fddm_profile_enable(int on);
+int64_t fddm_profile_read(char* buf, int64_t cap);
 
 /* ------------------------------------------------------------------------------------------------
  * a2  DiscreteDiffusionScheduler.q_sample                                     sched:31-50

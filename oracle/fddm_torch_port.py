@@ -1,7 +1,9 @@
 """CPU baseline port of the reference's token path in PyTorch-eager form.
 
 TEST / BENCH INFRASTRUCTURE ONLY (see oracle/fddm_oracle.py's header): only `tests/` and `bench.py`'s
-`cpu_baseline` / `--impl reference` legs import this file; nothing under `fddm-asr_b200/` does.
+baseline legs (`cpu_baseline`, `--impl reference`, and `eager_b200` = this same file run with device="cuda"
+as the "PyTorch-eager on B200" bar of SURVEY.md section 2b) import this file; nothing under `fddm-asr_b200/` does.
+Every function works on whatever device its inputs live on.
 
 The reference (TeemoCaption/FDDM-asr) is pure PyTorch and cannot travel to the GPU box, so the CPU arm
 of the benchmark times this restatement instead (`cpu_baseline.kind = "port"`).  It performs the same
@@ -42,7 +44,7 @@ def q_sample(x0_prob, t, alpha_bar, eps=1e-8):
 def sample_q(x0, t, alpha_bar, K):
     """train:180-188: ids -> one-hot -> q_sample -> multinomial."""
     B, L = x0.shape
-    oh = torch.zeros(B, L, K)
+    oh = torch.zeros(B, L, K, device=x0.device)
     oh.scatter_(-1, x0.unsqueeze(-1), 1.0)
     p = q_sample(oh, t, alpha_bar)
     return torch.multinomial(p.view(-1, K), 1).view(B, L)
@@ -53,8 +55,8 @@ def kl_term(xt, x0, logits, t, betas, x_mask=None):
     B, L, V = logits.shape
     dtype = logits.dtype
     xh = torch.softmax(logits, dim=-1)
-    xt_oh = torch.zeros(B, L, V, dtype=dtype).scatter_(-1, xt.unsqueeze(-1), 1.0)
-    x0_oh = torch.zeros(B, L, V, dtype=dtype).scatter_(-1, x0.unsqueeze(-1), 1.0)
+    xt_oh = torch.zeros(B, L, V, dtype=dtype, device=logits.device).scatter_(-1, xt.unsqueeze(-1), 1.0)
+    x0_oh = torch.zeros(B, L, V, dtype=dtype, device=logits.device).scatter_(-1, x0.unsqueeze(-1), 1.0)
     beta_t = betas[t - 1]
     beta_p = torch.where(t.eq(1), torch.zeros_like(beta_t), betas[(t - 2).clamp(min=0)])
     bt, bp = beta_t.view(B, 1, 1), beta_p.view(B, 1, 1)
@@ -84,8 +86,9 @@ def multistep_coeffs(t, delta, betas, K, T):
     """sched:132-183 as executed (aliased in-place recurrence, quirk Q1), scalar Python loop like
     the reference's."""
     B = t.shape[0]
-    a_c, b_c = torch.ones(B), torch.zeros(B)
-    a_g, b_g = torch.ones(B), torch.zeros(B)
+    dev = t.device
+    a_c, b_c = torch.ones(B, device=dev), torch.zeros(B, device=dev)
+    a_g, b_g = torch.ones(B, device=dev), torch.zeros(B, device=dev)
     tl = t.tolist()
     bl = betas.tolist()
     f32 = lambda x: torch.tensor(x, dtype=torch.float32)
@@ -129,8 +132,8 @@ def jump_once(x_t, logits, t_scalar, delta, betas, alpha_bar, K, T_train, T_infe
     B, L = x_t.shape
     p_x0 = torch.softmax(logits, dim=-1)
     if sampling_mode == "exact":
-        oh = torch.zeros(B, L, K).scatter_(-1, x_t.unsqueeze(-1), 1.0)
-        t_vec = torch.full((B,), t_scalar, dtype=torch.long)
+        oh = torch.zeros(B, L, K, device=x_t.device).scatter_(-1, x_t.unsqueeze(-1), 1.0)
+        t_vec = torch.full((B,), t_scalar, dtype=torch.long, device=x_t.device)
         p = q_posterior_multi_step(oh, p_x0.float(), t_vec, delta, betas, T_train)
     else:
         tgt = max(0, t_scalar - delta)
@@ -139,7 +142,7 @@ def jump_once(x_t, logits, t_scalar, delta, betas, alpha_bar, K, T_train, T_infe
         else:
             idx = int(round(max(1.0, min(float(T_train), tgt / float(max(1, T_infer)) * T_train))))
             ab = alpha_bar[idx]
-        p = ab * p_x0 + (1.0 - ab) * torch.full((1, 1, K), 1.0 / K, dtype=p_x0.dtype)
+        p = ab * p_x0 + (1.0 - ab) * torch.full((1, 1, K), 1.0 / K, dtype=p_x0.dtype, device=p_x0.device)
     if greedy:
         return p.argmax(dim=-1), p_x0
     if temperature != 1.0:

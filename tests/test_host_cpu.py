@@ -91,7 +91,7 @@ def test_dropin_shims_resolve_to_the_b200_implementation():
 def test_host_only_entry_points():
     import fddm_b200
     lib = fddm_b200._lib.lib
-    assert lib.fddm_version() == 2
+    assert lib.fddm_version() == 3
     assert lib.fddm_kl_workspace_bytes(32, 128) >= 128 + 32 * 128 * 4
     assert lib.fddm_kl_workspace_bytes(0, 5) == 0
     w = lib.fddm_lfd_workspace_bytes(32, 128, 768)
@@ -298,13 +298,19 @@ def test_batch_sharded_decomposition_gloo_world2():
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
-def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` prints ONE JSON line with the contract's keys (tiny workload)."""
+@pytest.mark.parametrize("force_port", [True, False])
+def test_bench_reference_arm_contract(force_port):
+    """`bench.py --impl reference` prints ONE JSON line with the contract's keys (tiny workload), through the
+    unmodified reference when it is importable here and through the port otherwise / when forced."""
     import json
     import subprocess
     import sys
+    env = dict(os.environ)
+    env.pop("FDDM_BASELINE", None)
+    if force_port:
+        env["FDDM_BASELINE"] = "port"
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
-                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -313,6 +319,9 @@ def test_bench_reference_arm_contract():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "slice" in d["cpu_baseline"]["sample"]
+    have_ref = any(p and os.path.exists(os.path.join(p, "fddm", "sched", "diffusion_scheduler.py"))
+                   for p in (os.environ.get("FDDM_REF"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")))
+    assert d["cpu_baseline"]["kind"] == ("reference" if (have_ref and not force_port) else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and "slice" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]

@@ -214,14 +214,16 @@ struct RingPlan {
   int ctas_per_sm;
   size_t smem_bytes;       // dynamic shared memory per CTA
 };
-static inline RingPlan plan_ring(size_t stage_bytes, int nt_consumers) {
+// `want_ctas` > 0: resident CTAs per SM the kernel was compiled for (falls back towards 1 while a CTA would
+// get fewer than two stages)
+static inline RingPlan plan_ring(size_t stage_bytes, int nt_consumers, int want_ctas = 0) {
   RingPlan p{};
   const size_t sb = (stage_bytes + 127) & ~size_t(127);
   const size_t budget_total = 216 * 1024;   // leave room for static smem + driver reservation
-  int ctas = (nt_consumers <= 256) ? 2 : 1;
+  int ctas = want_ctas > 0 ? want_ctas : ((nt_consumers <= 256) ? 2 : 1);
   size_t per = budget_total / ctas;
   int st = static_cast<int>(per / sb);
-  if (st < 2 && ctas == 2) { ctas = 1; per = budget_total; st = static_cast<int>(per / sb); }
+  while (st < 2 && ctas > 1) { --ctas; per = budget_total / ctas; st = static_cast<int>(per / sb); }
   if (st > kMaxStages) st = kMaxStages;
   p.nstages = st;          // may be 0 -> caller falls back / reports unsupported
   p.ctas_per_sm = ctas;

@@ -249,21 +249,29 @@ struct JumpRowCtx {
   bool identity;
 };
 
-// The production sampling path: in-kernel RNG, temperature 1.  Per element it costs a max, an
-// exp2 + add, and a multiply + add; everything else is O(1) per thread:
-//   * softmax statistics in one (max, sum) block reduction, p_k = exp(z_k - m_t) * (exp(m_t - m) / S)
+// The production sampling path: in-kernel RNG, temperature 1.  ONE block barrier per row.
+//   * per thread: m_t = max z, e_k = exp(z_k - m_t) kept in registers, s_t = sum e_k; per warp (shuffles):
+//     (m_w, s_w) with s_w relative to m_w; lane 0 publishes the pair; barrier; every thread derives the row's
+//     (m, S) from the NW pairs.  p_k = e_k * sc_t with sc_t = exp(m_t - m) / S.
 //   * the un-normalised target weights are affine in p_k (exact: w_k = A_k (a_g p_k + b_g sum p),
-//     fast: w_k = abar p_k + (1-abar)/K), so a thread's mass follows from its sum of p_k, its element
-//     count and -- for the owner of x_t -- one correction; no second pass over the entries
-//   * hierarchical exponential race: the minimum of independent exponentials with rates w_k is
-//     Exp(sum w_k) and its argmin is categorical in w_k, independent of the minimum.  Each thread races
-//     once with its mass (one Exp(1) variate per thread instead of one per vocab entry) and the winning
-//     thread picks among its own entries by inverse CDF.
+//     fast: w_k = abar p_k + (1-abar)/K), so the probability mass of a whole WARP follows from its s_w, its
+//     element count and -- for the warp that owns x_t -- one correction: every thread knows all NW warp masses
+//     right after that one barrier, without any further communication.
+//   * hierarchical inverse-CDF draw with three uniforms from ONE Philox call keyed by the row (all threads
+//     evaluate the same call, so they agree without talking): pick the warp from the NW warp masses; the other
+//     warps are done with the row; inside the picked warp pick the lane from the lane masses (shuffle prefix
+//     sum), then the entry among that lane's registers (gathered across the warp by shuffles, prefix sum,
+//     ballot).  The picked lane writes the id.  Same distribution as Categorical(probs=w/sum w).sample().
+// `wr` != nullptr (the last jump of a chain: p_x0 and its argmax are wanted) adds a pass that rounds p to the
+// logits dtype (quirk Q11), stores it, and one more block reduction for the argmax.
 template <int NT, typename T, class Row>
-__device__ __forceinline__ int jump_row_fast(Row& row, const JumpParams& p, const JumpRowCtx& c, const NoisePhilox& nz,
-                                             const float z_xt, RedRing& red, T* p_row_out, int* argmax_p) {
+__device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, const JumpRowCtx& c, const NoisePhilox& nz,
+                                              const float z_xt, RedRing& red, const int* s_nw, T* p_row_out,
+                                              int64_t* x_out_row, int64_t* argmax_out_row) {
   constexpr float kLog2e = 1.4426950408889634f;
+  constexpr int NW = NT / 32;
   const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float m_t = kNegInf;
   row.for_each([&](int, float& x) { m_t = fmaxf(m_t, x); });
   const float nm_t = -m_t * kLog2e;
@@ -272,65 +280,141 @@ __device__ __forceinline__ int jump_row_fast(Row& row, const JumpParams& p, cons
     x = ex2_approx(fmaf(x, kLog2e, nm_t));
     s_t += x;
   });
-  float m = m_t, S = s_t;
-  block_softmax_stats<NT>(m, S, red);
+  // warp-level (max, sum): max first, then the rescaled sums
+  float m_w = m_t;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, o));
+  const float f_tw = ex2_approx((m_t - m_w) * kLog2e);          // e_k are relative to m_t: rescale to m_w
+  float s_w = s_t * f_tw;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s_w += __shfl_xor_sync(0xffffffffu, s_w, o);
+  float* sc = red.next();
+  if (lane == 0) { sc[warp] = m_w; sc[32 + warp] = s_w; }
+  consumer_sync<NT>();
+  float m = sc[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) m = fmaxf(m, sc[w]);
+  float sw[NW];                                                 // warp sums relative to the row max
+  float S = 0.0f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    sw[w] = sc[32 + w] * ex2_approx((sc[w] - m) * kLog2e);
+    S += sw[w];
+  }
   const float inv_S = rcp_approx(S);
-  const float sc = ex2_approx((m_t - m) * kLog2e) * inv_S;
-  float psum = 0.0f;
-  if (argmax_p != nullptr) {
+  float rs = f_tw * ex2_approx((m_w - m) * kLog2e) * inv_S;      // p_k = (register) * rs
+  bool rounded = false;                                          // registers hold p rounded to T (rs == 1)
+
+  if (p_row_out != nullptr || argmax_out_row != nullptr) {
     float pm = -1.0f;
     int pm_k = 0x7fffffff;
     row.for_each([&](int k, float& x) {
-      x = Vec16<T>::round_trip(x * sc);
-      psum += x;
+      x = Vec16<T>::round_trip(x * rs);
       if (x > pm) { pm = x; pm_k = k; }
     });
-    block_argmax<NT>(pm, pm_k, red);
-    *argmax_p = pm_k;
-  } else {
-    row.for_each([&](int, float& x) {
-      x = Vec16<T>::round_trip(x * sc);
-      psum += x;
-    });
+    rs = 1.0f;
+    rounded = true;
+    if (p_row_out != nullptr) row.store(p_row_out, [](int, float x) { return x; });
+    if (argmax_out_row != nullptr) {
+      block_argmax<NT>(pm, pm_k, red);
+      if (threadIdx.x == 0) *argmax_out_row = pm_k;
+    }
   }
-  if (p.flags & FDDM_JUMP_WRITE_P) row.store(p_row_out, [](int, float x) { return x; });
-  if (c.identity) return c.xt;                                     // sched:133-134 (delta <= 0)
+  if (c.identity) {                                              // sched:133-134 (delta <= 0)
+    if (threadIdx.x == 0) *x_out_row = c.xt;
+    return;
+  }
 
-  // w_k = wa_k * p_k + wb_k with (wa, wb) = (A a_g, A b_g sum_p) [exact] or (abar, (1-abar)/K) [fast]
-  const float xh_xt = Vec16<T>::round_trip(ex2_approx(fmaf(z_xt, kLog2e, -m * kLog2e)) * inv_S);
-  const float sum_p = S * inv_S;
-  float wa, wb, wa_x, wb_x;                                        // generic entry / the entry k == x_t
+  // w_k = wa * p_k + wb, except (wa_x, wb_x) at k == x_t
+  const float p_xt = Vec16<T>::round_trip(ex2_approx(fmaf(z_xt, kLog2e, -m * kLog2e)) * inv_S);
+  float wa, wb, wa_x, wb_x;
   if (exact) {
-    const float bs = c.b_g * sum_p;                                // b_tgt * sum(x0hat)            sched:191
-    wa = c.b_c * c.a_g; wb = c.b_c * bs;                           // A = b_cum * sum_xt           sched:187
-    wa_x = (c.a_c + c.b_c) * c.a_g; wb_x = (c.a_c + c.b_c) * bs;   // A = a_cum + b_cum at x_t
+    const float bs = c.b_g;                                      // b_tgt * sum(x0hat), sum = 1     sched:191
+    wa = c.b_c * c.a_g; wb = c.b_c * bs;                         // A = b_cum * sum_xt             sched:187
+    wa_x = (c.a_c + c.b_c) * c.a_g; wb_x = (c.a_c + c.b_c) * bs; // A = a_cum + b_cum at x_t
   } else {
     wa = wa_x = c.ab;
-    wb = wb_x = (1.0f - c.ab) * p.u;                               // sampler:147-151
+    wb = wb_x = (1.0f - c.ab) * p.u;                             // sampler:147-151
   }
-  const bool owner = (row.owner_of(c.xt) == row.tid);
+  const float corr = fmaf(wa_x - wa, p_xt, wb_x - wb);           // extra mass of the entry k == x_t
+  const int owner = row.owner_of(c.xt);                          // thread that holds x_t
+  const uint4 rnd = philox4x32_10(make_uint4(0u, nz.row, nz.off.x, nz.off.y), nz.key);
+  constexpr float k2m24 = 1.0f / 16777216.0f;
+  // level 1: the warp
+  float tot = 0.0f;
+  float cw[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    float mw = fmaf(wa, sw[w] * inv_S, wb * static_cast<float>(s_nw[w]));
+    if (w == (owner >> 5)) mw += corr;
+    tot += fmaxf(mw, 0.0f);
+    cw[w] = tot;
+  }
+  const float t1 = tot * ((static_cast<float>(rnd.x >> 8) + 0.5f) * k2m24);
+  int wsel = NW - 1;
+#pragma unroll
+  for (int w = NW - 1; w >= 0; --w)
+    if (cw[w] >= t1 && (w == 0 ? cw[0] > 0.0f : cw[w] > cw[w - 1])) wsel = w;
+  if (warp != wsel) return;
+
+  // level 2: the lane (inclusive prefix sum of the lane masses)
+  float psum = s_t * rs;
+  if (rounded) {
+    psum = 0.0f;
+    row.for_each([&](int, float& x) { psum += x; });
+  }
   float mass = fmaf(wa, psum, wb * static_cast<float>(row.n_owned()));
-  if (owner) mass += fmaf(wa_x - wa, xh_xt, wb_x - wb);
-  const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(row.tid), nz.row, nz.off.x, nz.off.y), nz.key);
-  float best = __fdividef(mass, exp1_from_bits(rnd.x));
-  int best_k = row.tid;
-  block_argmax<NT>(best, best_k, red);
-  int picked = 0;
-  if (row.tid == best_k) {
-    const float target = mass * ((static_cast<float>(rnd.y >> 8) + 1.0f) * (1.0f / 16777216.0f));
-    float cum = 0.0f;
-    int chosen = -1, last_pos = c.xt;
-    row.for_each([&](int k, float& xh) {
-      const float w = (k == c.xt) ? fmaf(wa_x, xh, wb_x) : fmaf(wa, xh, wb);
-      if (chosen < 0 && w > 0.0f) {
-        cum += w;
-        last_pos = k;
-        if (cum >= target) chosen = k;
-      }
-    });
-    picked = (chosen < 0) ? last_pos : chosen;
+  if (row.tid == owner) mass += corr;
+  mass = fmaxf(mass, 0.0f);
+  float pre = mass;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += up;
   }
-  return block_broadcast_int<NT>(row.tid == best_k, picked, red);
+  const float wtot = __shfl_sync(0xffffffffu, pre, 31);
+  const float t2 = wtot * ((static_cast<float>(rnd.y >> 8) + 0.5f) * k2m24);
+  unsigned hit = __ballot_sync(0xffffffffu, pre >= t2 && mass > 0.0f);
+  if (hit == 0u) hit = __ballot_sync(0xffffffffu, mass > 0.0f);   // rounding pushed the target past the total
+  const int lsel = hit ? (__ffs(hit) - 1) : 0;
+
+  // level 3: the entry among the picked lane's registers, 32 at a time across the warp
+  const float rs_sel = __shfl_sync(0xffffffffu, rs, lsel);
+  const int tid_sel = (warp << 5) + lsel;
+  const float lane_mass = __shfl_sync(0xffffffffu, mass, lsel);
+  const float t3 = lane_mass * ((static_cast<float>(rnd.z >> 8) + 0.5f) * k2m24);
+  constexpr int N = Row::N, EPT = Row::NVEC * Row::N;
+  float base = 0.0f;
+  int chosen = -1, last_pos = -1;
+#pragma unroll
+  for (int r0 = 0; r0 < EPT; r0 += 32) {
+    float mine = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float v = __shfl_sync(0xffffffffu, row.v[r0 + r], lsel);
+      if (lane == r) mine = v;
+    }
+    const int reg = r0 + lane;
+    const int vi = (reg / N) * NT + tid_sel;
+    const int k = vi * N + (reg % N);
+    const bool valid = vi < row.nvec;
+    float w = 0.0f;
+    if (valid) w = (k == c.xt) ? fmaf(wa_x, mine * rs_sel, wb_x) : fmaf(wa, mine * rs_sel, wb);
+    w = fmaxf(w, 0.0f);
+    float pw = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, pw, o);
+      if (lane >= o) pw += up;
+    }
+    pw += base;
+    const unsigned pos = __ballot_sync(0xffffffffu, w > 0.0f);
+    const unsigned got = __ballot_sync(0xffffffffu, w > 0.0f && pw >= t3);
+    if (chosen < 0 && got != 0u) chosen = __shfl_sync(0xffffffffu, k, __ffs(got) - 1);
+    if (pos != 0u) last_pos = __shfl_sync(0xffffffffu, k, 31 - __clz(pos));
+    base = __shfl_sync(0xffffffffu, pw, 31);
+  }
+  if (lane == 0) *x_out_row = (chosen >= 0) ? chosen : (last_pos >= 0 ? last_pos : c.xt);
 }
 
 // One row: returns the new id (valid in every thread).  `NoiseT` provides E_k when sampling.
@@ -340,10 +424,6 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
   const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
   const bool sample = (p.flags & FDDM_JUMP_SAMPLE) != 0;
   const bool write_p = (p.flags & FDDM_JUMP_WRITE_P) != 0;
-  if constexpr (std::is_same<NoiseT, NoisePhilox>::value) {
-    if (sample && p.temperature == 1.0f) return jump_row_fast<NT, T>(row, p, c, nz, z_xt, red, p_row_out, argmax_p);
-  }
-
   // softmax in the logits dtype (F.softmax, sampler:189): exp(z-m)/S, rounded to T.
   // FAST (in-kernel RNG: the drawn ids cannot be compared with the reference's anyway) uses MUFU
   // ex2 and a multiply by 1/S; otherwise libm expf and an IEEE division so that the probabilities
@@ -531,13 +611,19 @@ __device__ __forceinline__ void jump_epilogue(const JumpParams& p, int tid) {
 }
 
 // fast path: TMA ring (logits row [+ noise row] per stage) + register-resident rows
+// resident CTAs per SM: the in-kernel-RNG flavour keeps few live registers besides the row itself, so three
+// 256-thread CTAs fit the register file (three rows in flight per SM instead of two)
+template <int NT, int NOISE>
+constexpr int jump_ctas_per_sm() { return NT <= 256 ? (NOISE == 2 ? 3 : 2) : 1; }
+
 template <typename T, int NT, int EPT, int NOISE /*0 none, 1 memory, 2 philox*/>
-__global__ void __launch_bounds__(NT + 32, (NT <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(NT + 32, jump_ctas_per_sm<NT, NOISE>())
 jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stage_bytes, const uint32_t noise_off) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages];
   __shared__ RingMeta s_meta[kMaxStages];
   __shared__ float s_red[kRedFloats];
+  __shared__ int s_nw[32];               // valid row entries owned by each consumer warp (row independent)
 
   Ring ring;
   ring.stages = dyn_smem;
@@ -584,6 +670,15 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
 
   RedRing red{s_red, 0};
   RegRow<T, NT, EPT> row;
+  row.tid = tid;
+  row.nvec = p.K / RegRow<T, NT, EPT>::N;
+  {
+    int n = row.n_owned();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((tid & 31) == 0) s_nw[tid >> 5] = n;       // read only after the first row's block barrier
+  }
+  const bool fast = (NOISE == 2) && p.temperature == 1.0f;
   int s = 0;
   uint32_t round = 0;
   for (;;) {
@@ -598,12 +693,16 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     if (NOISE != 1) ring_release(ring, s);
     T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K : nullptr;
     int amax = 0;
-    int id;
+    int id = 0;
     if (NOISE == 2) {
       NoisePhilox nz;
       philox_key_off(p.philox_state, p.key, p.off, nz.key, nz.off); nz.row = static_cast<uint32_t>(mt.row);
       nz.off.y ^= kJumpDomain;
-      id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
+      if (fast)
+        jump_row_fast<NT, T>(row, p, c, nz, z_xt, red, s_nw, p_row, p.x_out + mt.row,
+                             p.argmax_p_out ? p.argmax_p_out + mt.row : nullptr);
+      else
+        id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     } else {
       NoiseMem nz;
       nz.p = reinterpret_cast<const float*>(ring.stage(s) + noise_off);
@@ -611,7 +710,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
       id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
     }
     if (NOISE == 1) ring_release(ring, s);
-    if (tid == 0) {
+    if (tid == 0 && !fast) {
       p.x_out[mt.row] = id;
       if (p.argmax_p_out) p.argmax_p_out[mt.row] = amax;
     }
@@ -673,7 +772,7 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
     else if (p.K <= 16384) { nt = 512; ept = 32; }
     else { nt = 512; ept = 64; }
     const size_t row_pad = (row_bytes + 127) & ~size_t(127);
-    const RingPlan plan = plan_ring(row_pad + noise_bytes, nt);
+    const RingPlan plan = plan_ring(row_pad + noise_bytes, nt, (NOISE == 2 && nt <= 256) ? 3 : 0);
     if (plan.nstages >= 1) {
       const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
       const uint32_t sb = static_cast<uint32_t>((row_pad + noise_bytes + 127) & ~size_t(127));

@@ -328,6 +328,7 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
         mt.i1 = static_cast<int>(p.x0[row]);
         load_betas(p, row / p.L, mt.f0, mt.f1);
         mt.f2 = 0.0f; mt.f3 = 0.0f;
+        mt.r0 = mt.r1 = mt.r2 = 0u;
         ring.meta[s] = mt;
         if (w != 0.0f) {
           mbar_arrive_expect_tx(&ring.full[s], row_bytes);

@@ -175,6 +175,7 @@ struct RingMeta {          // one per stage, written by the producer before it a
   float w;                 // row weight (0 => nothing was loaded for this row)
   int i0, i1;              // per-kernel integers (token ids)
   float f0, f1, f2, f3;    // per-kernel scalars (schedule coefficients)
+  uint32_t r0, r1, r2;     // per-row random bits drawn by the producer (in-kernel RNG kernels)
 };
 
 struct Ring {
@@ -216,14 +217,14 @@ struct RingPlan {
 };
 // `want_ctas` > 0: resident CTAs per SM the kernel was compiled for (falls back towards 1 while a CTA would
 // get fewer than two stages)
-static inline RingPlan plan_ring(size_t stage_bytes, int nt_consumers, int want_ctas = 0) {
+static inline RingPlan plan_ring(size_t stage_bytes, int nt_consumers, int want_ctas = 0, int min_stages = 2) {
   RingPlan p{};
   const size_t sb = (stage_bytes + 127) & ~size_t(127);
   const size_t budget_total = 216 * 1024;   // leave room for static smem + driver reservation
   int ctas = want_ctas > 0 ? want_ctas : ((nt_consumers <= 256) ? 2 : 1);
   size_t per = budget_total / ctas;
   int st = static_cast<int>(per / sb);
-  while (st < 2 && ctas > 1) { --ctas; per = budget_total / ctas; st = static_cast<int>(per / sb); }
+  while (st < min_stages && ctas > 1) { --ctas; per = budget_total / ctas; st = static_cast<int>(per / sb); }
   if (st > kMaxStages) st = kMaxStages;
   p.nstages = st;          // may be 0 -> caller falls back / reports unsupported
   p.ctas_per_sm = ctas;

@@ -13,6 +13,8 @@
 // Elementwise steps that decide ids use __fmul_rn/__fadd_rn/__fdiv_rn so that nvcc cannot contract
 // them into FMAs: the op order is the reference's.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <type_traits>
@@ -243,6 +245,7 @@ namespace {
 constexpr uint32_t kJumpDomain = 0x4A554D50u;
 
 struct JumpRowCtx {
+  uint32_t r0, r1, r2;       // this row's random bits (drawn once per row by the producer)
   int xt;
   float a_c, b_c, a_g, b_g;  // exact
   float ab;                  // fast
@@ -265,21 +268,25 @@ struct JumpRowCtx {
 // `wr` != nullptr (the last jump of a chain: p_x0 and its argmax are wanted) adds a pass that rounds p to the
 // logits dtype (quirk Q11), stores it, and one more block reduction for the argmax.
 template <int NT, typename T, class Row>
-__device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, const JumpRowCtx& c, const NoisePhilox& nz,
-                                              const float z_xt, RedRing& red, const int* s_nw, T* p_row_out,
+__device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, const JumpRowCtx& c, const float z_xt, RedRing& red, const int* s_nw, T* p_row_out,
                                               int64_t* x_out_row, int64_t* argmax_out_row) {
   constexpr float kLog2e = 1.4426950408889634f;
   constexpr int NW = NT / 32;
   const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float m_t = kNegInf;
-  row.for_each([&](int, float& x) { m_t = fmaxf(m_t, x); });
+  // four independent accumulators: the chains are EPT/4 long instead of EPT
+  float mx[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
+  row.for_each4([&](float* x) { mx[0] = fmaxf(mx[0], x[0]); mx[1] = fmaxf(mx[1], x[1]);
+                                mx[2] = fmaxf(mx[2], x[2]); mx[3] = fmaxf(mx[3], x[3]); },
+                [&](float&) {});
+  const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
   const float nm_t = -m_t * kLog2e;
-  float s_t = 0.0f;
-  row.for_each([&](int, float& x) {
-    x = ex2_approx(fmaf(x, kLog2e, nm_t));
-    s_t += x;
-  });
+  float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  row.for_each4([&](float* x) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { x[e] = ex2_approx(fmaf(x[e], kLog2e, nm_t)); sx[e] += x[e]; }
+  }, [&](float&) {});
+  const float s_t = (sx[0] + sx[1]) + (sx[2] + sx[3]);
   // warp-level (max, sum): max first, then the rescaled sums
   float m_w = m_t;
 #pragma unroll
@@ -338,7 +345,6 @@ __device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, con
   }
   const float corr = fmaf(wa_x - wa, p_xt, wb_x - wb);           // extra mass of the entry k == x_t
   const int owner = row.owner_of(c.xt);                          // thread that holds x_t
-  const uint4 rnd = philox4x32_10(make_uint4(0u, nz.row, nz.off.x, nz.off.y), nz.key);
   constexpr float k2m24 = 1.0f / 16777216.0f;
   // level 1: the warp
   float tot = 0.0f;
@@ -350,7 +356,7 @@ __device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, con
     tot += fmaxf(mw, 0.0f);
     cw[w] = tot;
   }
-  const float t1 = tot * ((static_cast<float>(rnd.x >> 8) + 0.5f) * k2m24);
+  const float t1 = tot * ((static_cast<float>(c.r0 >> 8) + 0.5f) * k2m24);
   int wsel = NW - 1;
 #pragma unroll
   for (int w = NW - 1; w >= 0; --w)
@@ -373,7 +379,7 @@ __device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, con
     if (lane >= o) pre += up;
   }
   const float wtot = __shfl_sync(0xffffffffu, pre, 31);
-  const float t2 = wtot * ((static_cast<float>(rnd.y >> 8) + 0.5f) * k2m24);
+  const float t2 = wtot * ((static_cast<float>(c.r1 >> 8) + 0.5f) * k2m24);
   unsigned hit = __ballot_sync(0xffffffffu, pre >= t2 && mass > 0.0f);
   if (hit == 0u) hit = __ballot_sync(0xffffffffu, mass > 0.0f);   // rounding pushed the target past the total
   const int lsel = hit ? (__ffs(hit) - 1) : 0;
@@ -382,7 +388,7 @@ __device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, con
   const float rs_sel = __shfl_sync(0xffffffffu, rs, lsel);
   const int tid_sel = (warp << 5) + lsel;
   const float lane_mass = __shfl_sync(0xffffffffu, mass, lsel);
-  const float t3 = lane_mass * ((static_cast<float>(rnd.z >> 8) + 0.5f) * k2m24);
+  const float t3 = lane_mass * ((static_cast<float>(c.r2 >> 8) + 0.5f) * k2m24);
   constexpr int N = Row::N, EPT = Row::NVEC * Row::N;
   float base = 0.0f;
   int chosen = -1, last_pos = -1;
@@ -582,6 +588,7 @@ __device__ __forceinline__ int jump_row_math(Row& row, const JumpParams& p, cons
 __device__ __forceinline__ void jump_load_ctx(const JumpParams& p, int row, JumpRowCtx& c) {
   const int b = row / p.L;
   c.xt = static_cast<int>(p.x_t[row]);
+  c.r0 = c.r1 = c.r2 = 0u;
   c.identity = false;
   c.a_c = c.b_c = c.a_g = c.b_g = 0.0f;
   c.ab = 1.0f;
@@ -611,13 +618,10 @@ __device__ __forceinline__ void jump_epilogue(const JumpParams& p, int tid) {
 }
 
 // fast path: TMA ring (logits row [+ noise row] per stage) + register-resident rows
-// resident CTAs per SM: the in-kernel-RNG flavour keeps few live registers besides the row itself, so three
-// 256-thread CTAs fit the register file (three rows in flight per SM instead of two)
-template <int NT, int NOISE>
-constexpr int jump_ctas_per_sm() { return NT <= 256 ? (NOISE == 2 ? 3 : 2) : 1; }
-
-template <typename T, int NT, int EPT, int NOISE /*0 none, 1 memory, 2 philox*/>
-__global__ void __launch_bounds__(NT + 32, jump_ctas_per_sm<NT, NOISE>())
+// CTAS = resident CTAs per SM the kernel is compiled for (register budget): the in-kernel-RNG flavour keeps
+// few live registers besides the row itself, so more rows can be in flight per SM
+template <typename T, int NT, int EPT, int NOISE /*0 none, 1 memory, 2 philox*/, int CTAS>
+__global__ void __launch_bounds__(NT + 32, CTAS)
 jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stage_bytes, const uint32_t noise_off) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages];
@@ -650,18 +654,28 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
           mbar_arrive(&ring.full[s]);
           break;
         }
+        // the copies go out first; the row's metadata (and its random bits) are prepared under their latency;
+        // the stage becomes visible to the consumers only with the arrive at the end
+        mbar_expect_tx(&ring.full[s], row_bytes + (NOISE == 1 ? noise_bytes : 0u));
+        tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
+                    row_bytes, &ring.full[s]);
+        if (NOISE == 1)
+          tma_load_1d(ring.stage(s) + noise_off, p.noise + static_cast<size_t>(row) * p.K, noise_bytes, &ring.full[s]);
         JumpRowCtx c;
         jump_load_ctx(p, row, c);
         RingMeta mt;
         mt.row = row; mt.w = c.identity ? 0.0f : 1.0f; mt.i0 = c.xt; mt.i1 = 0;
         mt.f0 = (p.flags & FDDM_JUMP_EXACT) ? c.a_c : c.ab;
         mt.f1 = c.b_c; mt.f2 = c.a_g; mt.f3 = c.b_g;
+        mt.r0 = mt.r1 = mt.r2 = 0u;
+        if (NOISE == 2) {
+          uint2 key, off;
+          philox_key_off(p.philox_state, p.key, p.off, key, off);
+          const uint4 rnd = philox4x32_10(make_uint4(0xffffffffu, static_cast<uint32_t>(row), off.x, off.y ^ kJumpDomain), key);
+          mt.r0 = rnd.x; mt.r1 = rnd.y; mt.r2 = rnd.z;
+        }
         ring.meta[s] = mt;
-        mbar_arrive_expect_tx(&ring.full[s], row_bytes + (NOISE == 1 ? noise_bytes : 0u));
-        tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
-                    row_bytes, &ring.full[s]);
-        if (NOISE == 1)
-          tma_load_1d(ring.stage(s) + noise_off, p.noise + static_cast<size_t>(row) * p.K, noise_bytes, &ring.full[s]);
+        mbar_arrive(&ring.full[s]);
         if (++s == nstages) { s = 0; ++round; }
       }
     }
@@ -687,6 +701,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
     if (mt.row < 0) break;
     JumpRowCtx c;
     c.xt = mt.i0; c.identity = (mt.w == 0.0f);
+    c.r0 = mt.r0; c.r1 = mt.r1; c.r2 = mt.r2;
     c.a_c = mt.f0; c.ab = mt.f0; c.b_c = mt.f1; c.a_g = mt.f2; c.b_g = mt.f3;
     row.load_from_smem(ring.stage(s), p.K, tid);
     const float z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(ring.stage(s)) + c.xt);
@@ -699,7 +714,7 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
       philox_key_off(p.philox_state, p.key, p.off, nz.key, nz.off); nz.row = static_cast<uint32_t>(mt.row);
       nz.off.y ^= kJumpDomain;
       if (fast)
-        jump_row_fast<NT, T>(row, p, c, nz, z_xt, red, s_nw, p_row, p.x_out + mt.row,
+        jump_row_fast<NT, T>(row, p, c, z_xt, red, s_nw, p_row, p.x_out + mt.row,
                              p.argmax_p_out ? p.argmax_p_out + mt.row : nullptr);
       else
         id = jump_row_math<NT, T>(row, p, c, nz, z_xt, red, p_row, p.argmax_p_out ? &amax : nullptr);
@@ -766,27 +781,44 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
   const int sms = num_sms();
   KernelScope ks(NOISE == 0 ? "jump_rows_greedy" : (NOISE == 1 ? "jump_rows_injected_noise" : "jump_rows_philox"), stream);
   if (aligned && p.K <= 32768 && p.work != nullptr) {
-    int nt, ept;
-    if (p.K <= 4096) { nt = 128; ept = 32; }
-    else if (p.K <= 8192) { nt = 256; ept = 32; }
-    else if (p.K <= 16384) { nt = 512; ept = 32; }
-    else { nt = 512; ept = 64; }
+    // (consumer threads, row entries per thread, resident CTAs per SM).  The per-row fixed cost (reductions,
+    // barrier, draw) is per THREAD, so the in-kernel-RNG flavour uses few threads with many entries each.
+    int nt, ept, ctas;
+    if (p.K <= 4096) { nt = 128; ept = 32; ctas = (NOISE == 2) ? 4 : 2; }
+    else if (p.K <= 8192) { nt = (NOISE == 2) ? 128 : 256; ept = (NOISE == 2) ? 64 : 32; ctas = (NOISE == 2) ? 3 : 2; }
+    else if (p.K <= 16384) { nt = 512; ept = 32; ctas = 1; }
+    else { nt = 512; ept = 64; ctas = 1; }
+    int force_stages = 0;
+    if (const char* e = getenv("FDDM_JUMP_CFG")) {               // experiment knob: "NTxEPTxCTAS[xSTAGES]"
+      int a = 0, b = 0, c3 = 0, d = 0;
+      if (sscanf(e, "%dx%dx%dx%d", &a, &b, &c3, &d) >= 3 && NOISE == 2 && p.K <= 8192 && p.K > 4096) {
+        nt = a; ept = b; ctas = c3; force_stages = d;
+      }
+    }
     const size_t row_pad = (row_bytes + 127) & ~size_t(127);
-    const RingPlan plan = plan_ring(row_pad + noise_bytes, nt, (NOISE == 2 && nt <= 256) ? 3 : 0);
+    RingPlan plan = plan_ring(row_pad + noise_bytes, nt, ctas, force_stages == 1 ? 1 : 2);
+    if (force_stages > 0 && force_stages <= plan.nstages) {
+      plan.nstages = force_stages;
+      plan.smem_bytes = ((row_pad + noise_bytes + 127) & ~size_t(127)) * force_stages + 128;
+    }
     if (plan.nstages >= 1) {
       const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
       const uint32_t sb = static_cast<uint32_t>((row_pad + noise_bytes + 127) & ~size_t(127));
-#define FDDM_JUMP_LAUNCH(NT_, EPT_)                                                                         \
+#define FDDM_JUMP_LAUNCH(NT_, EPT_, CTAS_)                                                                  \
   do {                                                                                                      \
-    auto kfn = jump_rows_ring_kernel<T, NT_, EPT_, NOISE>;                                                  \
+    auto kfn = jump_rows_ring_kernel<T, NT_, EPT_, NOISE, CTAS_>;                                           \
     FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                       static_cast<int>(plan.smem_bytes)));                                  \
     kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb, static_cast<uint32_t>(row_pad));  \
   } while (0)
-      if (nt == 128) FDDM_JUMP_LAUNCH(128, 32);
-      else if (nt == 256) FDDM_JUMP_LAUNCH(256, 32);
-      else if (ept == 32) FDDM_JUMP_LAUNCH(512, 32);
-      else FDDM_JUMP_LAUNCH(512, 64);
+      if (NOISE == 2 && nt == 128 && ept == 32) FDDM_JUMP_LAUNCH(128, 32, 4);
+      else if (NOISE == 2 && nt == 128 && ept == 64 && ctas == 4) FDDM_JUMP_LAUNCH(128, 64, 4);
+      else if (NOISE == 2 && nt == 128 && ept == 64) FDDM_JUMP_LAUNCH(128, 64, 3);
+      else if (NOISE == 2 && nt == 256 && ept == 32) FDDM_JUMP_LAUNCH(256, 32, 3);
+      else if (nt == 128) FDDM_JUMP_LAUNCH(128, 32, 2);
+      else if (nt == 256) FDDM_JUMP_LAUNCH(256, 32, 2);
+      else if (ept == 32) FDDM_JUMP_LAUNCH(512, 32, 1);
+      else FDDM_JUMP_LAUNCH(512, 64, 1);
 #undef FDDM_JUMP_LAUNCH
       FDDM_LAUNCH_OK();
       return FDDM_OK;

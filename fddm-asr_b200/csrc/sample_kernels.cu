@@ -734,6 +734,266 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
   jump_epilogue<NT>(p, tid);
 }
 
+// ------------------------------------------------------------------------------------------------
+// In-kernel-RNG production kernel ("streamed"): the row is never held in registers.  One shared-memory
+// stage per CTA; the consumers stream over it twice (max, then exp-sum), release it -- the producer's
+// next copy then runs under the reductions and the draw -- and the ONE lane that finally needs individual
+// entries (the picked lane of the picked warp) re-reads its <= 16 vectors from global memory, where the
+// row was streamed microseconds ago (an L2 hit).  ~40 registers per thread instead of ~100, so the number
+// of resident CTAs -- rows in flight per SM -- is set by shared memory (6 at V=8000 fp32) and not by the
+// register file (4): per-row latency (barrier, reductions, draw) is what bounded the register-resident
+// kernel, measured 0.52-0.67 of HBM peak at 3-4 CTAs.  One block barrier per row; hierarchical
+// inverse-CDF draw as in jump_row_fast.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NT, int CTAS>
+__global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const JumpParams p) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ uint64_t s_full, s_empty;
+  __shared__ RingMeta s_meta;
+  __shared__ float s_red[kRedFloats];
+  __shared__ int s_nw[32];
+  constexpr int N = Vec16<T>::N, NW = NT / 32;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float k2m24 = 1.0f / 16777216.0f;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&s_full, 1);
+    mbar_init(&s_empty, NW);
+    mbar_fence_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  const uint32_t row_bytes = static_cast<uint32_t>(p.K) * sizeof(T);
+  const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
+
+  if (tid >= NT) {
+    if (tid == NT) {                       // producer lane
+      for (uint32_t it = 0;; ++it) {
+        if (it > 0) mbar_wait_backoff(&s_empty, (it - 1) & 1);
+        const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
+        if (row >= p.rows) {
+          s_meta.row = -1;
+          mbar_arrive(&s_full);
+          break;
+        }
+        mbar_expect_tx(&s_full, row_bytes);
+        tma_load_1d(dyn_smem, static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes, row_bytes,
+                    &s_full);
+        JumpRowCtx c;
+        jump_load_ctx(p, row, c);
+        RingMeta mt;
+        mt.row = row; mt.w = c.identity ? 0.0f : 1.0f; mt.i0 = c.xt; mt.i1 = 0;
+        mt.f0 = exact ? c.a_c : c.ab;
+        mt.f1 = c.b_c; mt.f2 = c.a_g; mt.f3 = c.b_g;
+        uint2 key, off;
+        philox_key_off(p.philox_state, p.key, p.off, key, off);
+        const uint4 rnd = philox4x32_10(make_uint4(0xffffffffu, static_cast<uint32_t>(row), off.x, off.y ^ kJumpDomain), key);
+        mt.r0 = rnd.x; mt.r1 = rnd.y; mt.r2 = rnd.z;
+        s_meta = mt;
+        mbar_arrive(&s_full);
+      }
+    }
+    return;
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nvec = p.K / N;
+  const int n_own_vec = (nvec - tid + NT - 1) / NT > 0 ? (nvec - tid + NT - 1) / NT : 0;
+  {
+    int n = n_own_vec * N;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) s_nw[warp] = n;         // read only after the first row's block barrier
+  }
+  RedRing red{s_red, 0};
+  const uint4* sv = reinterpret_cast<const uint4*>(dyn_smem);
+  const bool need_p = (p.flags & FDDM_JUMP_WRITE_P) != 0 || p.argmax_p_out != nullptr;
+
+  for (uint32_t it = 0;; ++it) {
+    mbar_wait(&s_full, it & 1);
+    const RingMeta mt = s_meta;
+    if (mt.row < 0) break;
+    const int xt = mt.i0;
+    // pass 1: thread max (four independent chains)
+    float mx[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      float f[N];
+      Vec16<T>::unpack(sv[vi], f);
+#pragma unroll
+      for (int e = 0; e < N; ++e) mx[e & 3] = fmaxf(mx[e & 3], f[e]);
+    }
+    const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    // pass 2: thread sum of exp(z - m_t)
+    const float nm_t = -m_t * kLog2e;
+    float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      float f[N];
+      Vec16<T>::unpack(sv[vi], f);
+#pragma unroll
+      for (int e = 0; e < N; ++e) sx[e & 3] += ex2_approx(fmaf(f[e], kLog2e, nm_t));
+    }
+    const float s_t = (sx[0] + sx[1]) + (sx[2] + sx[3]);
+    const float z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(dyn_smem) + xt);
+    if (!need_p) {                         // hand the stage back: the next row's copy starts now
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty);
+    }
+    // warp (max, sum), one block barrier, row (m, S) and the warp masses in every thread
+    float m_w = m_t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, o));
+    const float f_tw = ex2_approx((m_t - m_w) * kLog2e);
+    float s_w = s_t * f_tw;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s_w += __shfl_xor_sync(0xffffffffu, s_w, o);
+    float* sc = red.next();
+    if (lane == 0) { sc[warp] = m_w; sc[32 + warp] = s_w; }
+    consumer_sync<NT>();
+    float m = sc[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = fmaxf(m, sc[w]);
+    float sw[NW];
+    float S = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      sw[w] = sc[32 + w] * ex2_approx((sc[w] - m) * kLog2e);
+      S += sw[w];
+    }
+    const float inv_S = rcp_approx(S);
+    const float nm = -m * kLog2e;
+
+    if (need_p) {                          // last jump of a chain: p_x0 in the logits dtype (Q11) and its argmax
+      T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K : nullptr;
+      float pm = -1.0f;
+      int pm_k = 0x7fffffff;
+#pragma unroll 2
+      for (int vi = tid; vi < nvec; vi += NT) {
+        float f[N];
+        Vec16<T>::unpack(sv[vi], f);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          f[e] = Vec16<T>::round_trip(ex2_approx(fmaf(f[e], kLog2e, nm)) * inv_S);
+          if (f[e] > pm) { pm = f[e]; pm_k = vi * N + e; }
+        }
+        if (p_row) stg_stream_v4(reinterpret_cast<uint4*>(p_row) + vi, Vec16<T>::pack(f));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty);
+      if (p.argmax_p_out) {
+        block_argmax<NT>(pm, pm_k, red);
+        if (tid == 0) p.argmax_p_out[mt.row] = pm_k;
+      }
+    }
+    if (mt.w == 0.0f) {                    // sched:133-134 (delta <= 0): identity
+      if (tid == 0) p.x_out[mt.row] = xt;
+      continue;
+    }
+
+    // w_k = wa * p_k + wb, except (wa_x, wb_x) at k == x_t
+    const float p_xt = ex2_approx(fmaf(z_xt, kLog2e, nm)) * inv_S;
+    float wa, wb, wa_x, wb_x;
+    if (exact) {
+      const float a_c = mt.f0, b_c = mt.f1, a_g = mt.f2, b_g = mt.f3;
+      wa = b_c * a_g; wb = b_c * b_g;                             // A = b_cum * sum_xt, B = a_tgt p + b_tgt * 1
+      wa_x = (a_c + b_c) * a_g; wb_x = (a_c + b_c) * b_g;         // A = a_cum + b_cum at x_t   sched:187-191
+    } else {
+      wa = wa_x = mt.f0;
+      wb = wb_x = (1.0f - mt.f0) * p.u;                           // sampler:147-151
+    }
+    const float corr = fmaf(wa_x - wa, p_xt, wb_x - wb);
+    const int owner = (xt / N) % NT;
+    float tot = 0.0f;
+    float cw[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      float mw = fmaf(wa, sw[w] * inv_S, wb * static_cast<float>(s_nw[w]));
+      if (w == (owner >> 5)) mw += corr;
+      tot += fmaxf(mw, 0.0f);
+      cw[w] = tot;
+    }
+    const float t1 = tot * ((static_cast<float>(mt.r0 >> 8) + 0.5f) * k2m24);
+    int wsel = NW - 1;
+#pragma unroll
+    for (int w = NW - 1; w >= 0; --w)
+      if (cw[w] >= t1 && (w == 0 ? cw[0] > 0.0f : cw[w] > cw[w - 1])) wsel = w;
+    if (warp != wsel) continue;
+
+    // the picked warp: lane masses -> lane
+    float mass = fmaf(wa, s_t * f_tw * ex2_approx((m_w - m) * kLog2e) * inv_S, wb * static_cast<float>(n_own_vec * N));
+    if (tid == owner) mass += corr;
+    mass = fmaxf(mass, 0.0f);
+    float pre = mass;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += up;
+    }
+    const float wtot = __shfl_sync(0xffffffffu, pre, 31);
+    const float t2 = wtot * ((static_cast<float>(mt.r1 >> 8) + 0.5f) * k2m24);
+    unsigned hit = __ballot_sync(0xffffffffu, pre >= t2 && mass > 0.0f);
+    if (hit == 0u) hit = __ballot_sync(0xffffffffu, mass > 0.0f);
+    const int lsel = hit ? (__ffs(hit) - 1) : 0;
+    const int tid_sel = (warp << 5) + lsel;
+    const float lane_mass = __shfl_sync(0xffffffffu, mass, lsel);
+    const float t3 = lane_mass * ((static_cast<float>(mt.r2 >> 8) + 0.5f) * k2m24);
+    const int nv_sel = __shfl_sync(0xffffffffu, n_own_vec, lsel);
+
+    // the picked lane's entries: its vectors are re-read from global memory, one per lane
+    const uint4* grow = reinterpret_cast<const uint4*>(static_cast<const T*>(p.logits) + static_cast<size_t>(mt.row) * p.K);
+    float base = 0.0f;
+    int chosen = -1, last_pos = -1;
+    for (int j0 = 0; j0 < nv_sel; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < nv_sel;
+      const int vi = j * NT + tid_sel;
+      float w[N];
+      float lsum = 0.0f;
+      if (valid) {
+        float f[N];
+        Vec16<T>::unpack(__ldg(grow + vi), f);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const float pk = ex2_approx(fmaf(f[e], kLog2e, nm)) * inv_S;
+          w[e] = fmaxf((vi * N + e == xt) ? fmaf(wa_x, pk, wb_x) : fmaf(wa, pk, wb), 0.0f);
+          lsum += w[e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < N; ++e) w[e] = 0.0f;
+      }
+      float pw = lsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, pw, o);
+        if (lane >= o) pw += up;
+      }
+      pw += base;
+      // this lane's own pick, should the target fall into its vector
+      const float tl = t3 - (pw - lsum);
+      float cum = 0.0f;
+      int pick = -1, lastk = -1;
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        if (w[e] > 0.0f) {
+          cum += w[e];
+          lastk = vi * N + e;
+          if (pick < 0 && cum >= tl) pick = lastk;
+        }
+      }
+      if (pick < 0) pick = lastk;
+      const unsigned pos = __ballot_sync(0xffffffffu, lsum > 0.0f);
+      const unsigned got = __ballot_sync(0xffffffffu, lsum > 0.0f && pw >= t3);
+      if (chosen < 0 && got != 0u) chosen = __shfl_sync(0xffffffffu, pick, __ffs(got) - 1);
+      if (pos != 0u) last_pos = __shfl_sync(0xffffffffu, lastk, 31 - __clz(pos));
+      base = __shfl_sync(0xffffffffu, pw, 31);
+    }
+    if (lane == 0) p.x_out[mt.row] = (chosen >= 0) ? chosen : (last_pos >= 0 ? last_pos : xt);
+  }
+  jump_epilogue<NT>(p, tid);
+}
+
 // generic path
 template <typename T, int NT, int NOISE>
 __global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpParams p) {
@@ -780,6 +1040,34 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
   if (NOISE == 1) aligned = aligned && (noise_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
   const int sms = num_sms();
   KernelScope ks(NOISE == 0 ? "jump_rows_greedy" : (NOISE == 1 ? "jump_rows_injected_noise" : "jump_rows_philox"), stream);
+  if (NOISE == 2 && aligned && p.temperature == 1.0f && p.work != nullptr && getenv("FDDM_JUMP_CFG") == nullptr) {
+    // streamed kernel: one stage per CTA, resident CTAs limited by shared memory
+    const size_t stage = ((row_bytes + 127) & ~size_t(127)) + 128;
+    int ctas = static_cast<int>((216 * 1024) / (stage + 2048));
+    if (const char* e = getenv("FDDM_JUMP_CTAS")) ctas = std::min(ctas, atoi(e));      // experiment knob
+    if (ctas >= 2) {
+      ctas = std::min(ctas, 6);
+      const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * ctas));
+      const int nvec = p.K / Vec16<T>::N;
+#define FDDM_JUMP_STREAMED(NT_, CTAS_)                                                                      \
+  do {                                                                                                      \
+    auto kfn = jump_rows_streamed_kernel<T, NT_, CTAS_>;                                                    \
+    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage))); \
+    kfn<<<grid, NT_ + 32, stage, stream>>>(p);                                                              \
+  } while (0)
+      if (nvec <= 2048) {
+        if (ctas >= 6) FDDM_JUMP_STREAMED(128, 6);
+        else if (ctas >= 4) FDDM_JUMP_STREAMED(128, 4);
+        else FDDM_JUMP_STREAMED(128, 2);
+      } else {
+        if (ctas >= 4) FDDM_JUMP_STREAMED(256, 4);
+        else FDDM_JUMP_STREAMED(256, 2);
+      }
+#undef FDDM_JUMP_STREAMED
+      FDDM_LAUNCH_OK();
+      return FDDM_OK;
+    }
+  }
   if (aligned && p.K <= 32768 && p.work != nullptr) {
     // (consumer threads, row entries per thread, resident CTAs per SM).  The per-row fixed cost (reductions,
     // barrier, draw) is per THREAD, so the in-kernel-RNG flavour uses few threads with many entries each.

@@ -296,12 +296,13 @@ class ResidentDecoder:
         return self.logits
 
 
-def shard_check(fb, dev, group, world, rank, bn_allreduce="moment"):
+def shard_check(fb, dev, group, world, rank, per_rank_b=8):
     """world>1 only: the batch-sharded kl_term / lfd_loss (values AND gradients, through the same host classes
     the timed step uses) must equal this library's single-process evaluation of the whole batch (which the
-    -m gpu parity tests pin to the oracle).  Small batch; every rank builds the same global batch."""
+    -m gpu parity tests pin to the oracle).  Small batch; every rank builds the same global batch.
+    per_rank_b = 8 exercises the small-batch L_fd path (B < 32 per rank), 32 the tb-major one."""
     dist = torch.distributed
-    Bg, L, V, D, T = 8 * world, 32, 4000, 256, 200
+    Bg, L, V, D, T = per_rank_b * world, 32, 4000, 256, 200
     g = torch.Generator(device=dev).manual_seed(1)
     logits = torch.randn(Bg, L, V, generator=g, device=dev) * 2
     x0 = torch.randint(0, V, (Bg, L), generator=g, device=dev)
@@ -318,7 +319,7 @@ def shard_check(fb, dev, group, world, rank, bn_allreduce="moment"):
     (kl_ref + 0.5 * lf_ref).backward()
     lgs = logits[sl].clone().requires_grad_(True); a_s = za[sl].clone().requires_grad_(True); b_s = zb[sl].clone().requires_grad_(True)
     kl = fb.SchedulerAdapter(sch, group=group).kl_term(xt[sl], x0[sl], lgs, t[sl], mask[sl])
-    op = fb.LfdPipeline(a_s, b_s, LAMBDA, group=group, bn_allreduce=bn_allreduce)
+    op = fb.LfdPipeline(a_s, b_s, LAMBDA, group=group)
     op.stats(); op.xcov()
     lf = op.loss()
     (kl + 0.5 * lf).backward()
@@ -335,8 +336,7 @@ def shard_check(fb, dev, group, world, rank, bn_allreduce="moment"):
     worst = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
     tol = 2e-5
-    return {"ok": bool(float(worst) < tol), "tol": tol, "worst_over_ranks": float(worst), "bn_allreduce": bn_allreduce,
-            "global_batch": Bg, **{k: float(f"{v:.3e}") for k, v in errs.items()}}
+    return {"ok": bool(float(worst) < tol), "tol": tol, "worst_over_ranks": float(worst), "global_batch": Bg, **{k: float(f"{v:.3e}") for k, v in errs.items()}}
 
 
 def kernel_roofline(prof, n_steps, shp, dtype_name, valid_rows, pk, sampler_jumps):
@@ -404,7 +404,10 @@ def run_gpu(args):
 
     shard = None
     if world > 1:
-        shard = shard_check(fb, dev, group, world, rank)
+        shard = shard_check(fb, dev, group, world, rank, per_rank_b=32)      # the path the timed step takes
+        if shard["ok"]:
+            small = shard_check(fb, dev, group, world, rank, per_rank_b=8)   # and the small-batch path
+            shard = {**shard, "small_batch_path": small, "ok": small["ok"]}
         if not shard["ok"]:
             if rank == 0:
                 print(json.dumps({"error": "shard_check failed: the batch-sharded path disagrees with the whole-batch "

@@ -37,6 +37,26 @@ constexpr int kPackPad = 256;      // packed planes are zero-padded to multiples
 
 __host__ __device__ inline int64_t pack_pad(int64_t x) { return (x + kPackPad - 1) / kPackPad * kPackPad; }
 
+// Row order of the packed z~ planes.
+//   B >= 32 ("tb-major"): packed row r = t * Bp + b with the batch padded to Bp = ceil32(B) (rows b >= B are
+//     zero), so 32 consecutive packed rows -- the rows one epilogue warp of the backward contraction owns --
+//     always belong to ONE position t: the batch sums of dz~ * z~ the batch-norm backward needs come out of the
+//     contraction's epilogue as [T][Bp/32][D] partials instead of a separate pass over dz~ and z.
+//   B < 32 (the reference's own configs use B = 2..16): natural order r = b * T + t, nothing is padded, and the
+//     batch sums are taken by lfd_bn_reduce_kernel.
+struct LfdRows {
+  int B, T, Bp;
+  bool tb_major;
+  int64_t rows_packed;     // T * Bp (tb-major) or B * T
+  __host__ __device__ LfdRows(int64_t B_, int64_t T_) {
+    B = static_cast<int>(B_); T = static_cast<int>(T_);
+    tb_major = B_ >= 32;
+    Bp = tb_major ? static_cast<int>((B_ + 31) / 32 * 32) : B;
+    rows_packed = tb_major ? T_ * Bp : B_ * T_;
+  }
+  __host__ __device__ int parts() const { return tb_major ? Bp / 32 : 1; }   // bn partials per (t, d)
+};
+
 struct PackedOperand {
   const __nv_bfloat16* hi;
   const __nv_bfloat16* lo;   // residual plane (may be null when terms == 1)
@@ -49,6 +69,13 @@ struct PackedOperand {
 int umma_gemm(const PackedOperand& A, const PackedOperand& B, int64_t M, int64_t N, int64_t K, int splits, int terms,
               float alpha, float* out, int64_t out_ld, int64_t out_split_stride, cudaStream_t stream);
 
+// Backward contraction for tb-major planes (lfd_umma_bwd.cu), persistent CTAs, two TMEM accumulators:
+//   dz[b][t][n] = alpha * sum_k Z(r, k) * G(n, k)                 r = t * Bp + b, fp32, natural [B][T][D] order
+//   partial[r / 32][n] = sum over the 32 rows of dz * Zs(r, n)     Zs = the z~ planes of the tensor dz belongs to
+// Z, Zs: packed z~ planes (hi + lo), G: packed planes of G or G^T (hi + lo); N = K = D.
+int umma_bwd_gemm(const PackedOperand& Z, const PackedOperand& G, const PackedOperand& Zs, const LfdRows& rows, int64_t D,
+                  float alpha, float* dz, float* partial, cudaStream_t stream);
+
 // ---- workspace layout (bytes), shared by lfd_kernels.cu and lfd_umma.cu -------------------------
 struct LfdWorkspace {
   static constexpr size_t kCounters = 256;            // self-resetting unsigned counters
@@ -59,7 +86,7 @@ struct LfdWorkspace {
   __host__ __device__ LfdWorkspace(int64_t B, int64_t T, int64_t D) {
     const size_t td = static_cast<size_t>(T) * D, rows = static_cast<size_t>(B) * T;
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t Rp = static_cast<size_t>(pack_pad(rows)), Dp = static_cast<size_t>(pack_pad(D));
+    const size_t Rp = static_cast<size_t>(pack_pad(LfdRows(B, T).rows_packed)), Dp = static_cast<size_t>(pack_pad(D));
     plane_bytes = Rp * Dp * 2;
     gplane_bytes = Dp * Dp * 2;
     off_partials = kCounters;

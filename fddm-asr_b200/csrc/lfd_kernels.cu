@@ -72,6 +72,67 @@ __global__ void __launch_bounds__(256) lfd_stats_kernel(const T* __restrict__ za
   }
 }
 
+// Same moments, one CTA per (position t, strip of 64 column vectors, tensor): thread (tx, ty) owns column vector
+// tx and the batch rows ty, ty+4, ...; the four row groups are combined through shared memory in a fixed order
+// and written directly -- no atomics, no memset, and per thread U 16-byte loads in flight at a 1 KB stride
+// pattern DRAM likes.  Needs D % N == 0 and 16-byte aligned inputs.  grid = (ceil(D/(64 N)), T, 2).
+template <typename T>
+__global__ void __launch_bounds__(256) lfd_stats_rows_kernel(const T* __restrict__ za, const T* __restrict__ zb, int B,
+                                                             int Tn, int D, double* __restrict__ sums) {
+  constexpr int N = Vec16<T>::N;
+  __shared__ double s_part[3][2][64][N];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int t = blockIdx.y;
+  const int c = (blockIdx.x * 64 + tx) * N;
+  const T* z = (blockIdx.z == 0 ? za : zb) + static_cast<int64_t>(t) * D + c;
+  const int64_t bstride = static_cast<int64_t>(Tn) * D;
+  double s[N], q[N];
+#pragma unroll
+  for (int e = 0; e < N; ++e) { s[e] = 0.0; q[e] = 0.0; }
+  if (c < D) {
+    constexpr int U = 4;
+    int b = ty;
+    for (; b + 4 * (U - 1) < B; b += 4 * U) {
+      float x[U][N];
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec16<T>::unpack(ldg_stream_v4(z + (b + 4 * u) * bstride), x[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const double d = static_cast<double>(x[u][e]);
+          s[e] += d;
+          q[e] = fma(d, d, q[e]);
+        }
+      }
+    }
+    for (; b < B; b += 4) {
+      float x[N];
+      Vec16<T>::unpack(ldg_stream_v4(z + b * bstride), x);
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const double d = static_cast<double>(x[e]);
+        s[e] += d;
+        q[e] = fma(d, d, q[e]);
+      }
+    }
+  }
+  if (ty > 0) {
+#pragma unroll
+    for (int e = 0; e < N; ++e) { s_part[ty - 1][0][tx][e] = s[e]; s_part[ty - 1][1][tx][e] = q[e]; }
+  }
+  __syncthreads();
+  if (ty == 0 && c < D) {
+    const int64_t TD = static_cast<int64_t>(Tn) * D;
+    double* out_s = sums + static_cast<int64_t>(blockIdx.z) * 2 * TD + static_cast<int64_t>(t) * D + c;
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      out_s[e] = ((s[e] + s_part[0][0][tx][e]) + s_part[1][0][tx][e]) + s_part[2][0][tx][e];
+      out_s[TD + e] = ((q[e] + s_part[0][1][tx][e]) + s_part[1][1][tx][e]) + s_part[2][1][tx][e];
+    }
+  }
+}
+
 // sums -> (scale = rstd, shift = -mean*rstd) fp32 tables for both tensors: tables[4][TD]
 __global__ void __launch_bounds__(256) lfd_tables_kernel(const double* __restrict__ sums, int64_t TD, double n_batch,
                                                          double eps, float* __restrict__ tables) {
@@ -190,6 +251,107 @@ __global__ void __launch_bounds__(256) lfd_pack_kernel(const T* __restrict__ za,
   }
 }
 
+// tb-major variant (B >= 32, lfd_common.cuh): packed row r = t * Bp + b.  A CTA owns one position t and one
+// 64-column strip and walks the batch 32 rows at a time, so every thread touches the SAME columns in every
+// iteration: the standardisation scale/shift of (t, column) are loaded once per CTA into registers instead of
+// once per element.  Rows b >= B (batch padding) and, for the last t, the rows up to R_pad are written as zeros.
+// grid = (D_pad/64, T).
+template <typename T>
+__global__ void __launch_bounds__(256) lfd_pack_tb_kernel(const T* __restrict__ za, const T* __restrict__ zb,
+                                                          const float* __restrict__ tables, int Bn, int Bp, int Tn, int D,
+                                                          int64_t R_pad, __nv_bfloat16* __restrict__ a_hi,
+                                                          __nv_bfloat16* __restrict__ a_lo, __nv_bfloat16* __restrict__ b_hi,
+                                                          __nv_bfloat16* __restrict__ b_lo, double* __restrict__ diag) {
+  __shared__ __align__(16) float sA[32][kPackLd];
+  __shared__ __align__(16) float sB[32][kPackLd];
+  constexpr int N = Vec16<T>::N;                 // elements per 16-byte global vector
+  constexpr int VPR = 64 / N;                    // vectors per tile row
+  constexpr int RPI = 256 / VPR;                 // tile rows covered by one sweep of the 256 threads
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.y;
+  const int c0 = blockIdx.x * 64;
+  const int cc = blockIdx.x * 8 + warp;          // this warp's chunk column in phase B
+  const int64_t TD = static_cast<int64_t>(Tn) * D;
+  // phase-A role of this thread: column vector cv of the strip (fixed), tile rows prow, prow + RPI, ...
+  const int cv = threadIdx.x % VPR, prow = threadIdx.x / VPR;
+  const int c = c0 + cv * N;
+  const bool col_ok = c < D;
+  float sca[N], sha[N], scb[N], shb[N];
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+    const int64_t so = static_cast<int64_t>(t) * D + c + e;
+    sca[e] = col_ok ? __ldg(tables + so) : 0.0f;
+    sha[e] = col_ok ? __ldg(tables + TD + so) : 0.0f;
+    scb[e] = col_ok ? __ldg(tables + 2 * TD + so) : 0.0f;
+    shb[e] = col_ok ? __ldg(tables + 3 * TD + so) : 0.0f;
+  }
+  double acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+  const int64_t rbase = static_cast<int64_t>(t) * Bp;
+  // the last position also zero-fills the plane rows between T*Bp and R_pad
+  const int nrows = (t == Tn - 1) ? static_cast<int>(R_pad - rbase) : Bp;
+  for (int b0 = 0; b0 < nrows; b0 += 32) {
+#pragma unroll
+    for (int rr = prow; rr < 32; rr += RPI) {
+      const int b = b0 + rr;
+      float xa[N], xb[N];
+      if (b < Bn && col_ok) {
+        const int64_t off = (static_cast<int64_t>(b) * Tn + t) * D + c;
+        Vec16<T>::unpack(ldg_stream_v4(za + off), xa);
+        Vec16<T>::unpack(ldg_stream_v4(zb + off), xb);
+#pragma unroll
+        for (int e = 0; e < N; ++e) { xa[e] = fmaf(xa[e], sca[e], sha[e]); xb[e] = fmaf(xb[e], scb[e], shb[e]); }
+      } else {
+#pragma unroll
+        for (int e = 0; e < N; ++e) { xa[e] = 0.0f; xb[e] = 0.0f; }
+      }
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) {
+        *reinterpret_cast<float4*>(&sA[rr][cv * N + 4 * q]) = make_float4(xa[4 * q], xa[4 * q + 1], xa[4 * q + 2], xa[4 * q + 3]);
+        *reinterpret_cast<float4*>(&sB[rr][cv * N + 4 * q]) = make_float4(xb[4 * q], xb[4 * q + 1], xb[4 * q + 2], xb[4 * q + 3]);
+      }
+    }
+    __syncthreads();
+    float a[8], b[8];
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[lane][warp * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[lane][warp * 8 + 4]);
+      const float4 b0v = *reinterpret_cast<const float4*>(&sB[lane][warp * 8]);
+      const float4 b1v = *reinterpret_cast<const float4*>(&sB[lane][warp * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0v.x; b[1] = b0v.y; b[2] = b0v.z; b[3] = b0v.w; b[4] = b1v.x; b[5] = b1v.y; b[6] = b1v.z; b[7] = b1v.w;
+    }
+    __syncthreads();                                         // tiles are rewritten by the next iteration
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += static_cast<double>(a[e]) * static_cast<double>(b[e]);   // pads are 0
+    const int64_t off = (static_cast<int64_t>(cc) * R_pad + rbase + b0 + lane) * 8;                // elements
+    const uint4 ah = Vec16<__nv_bfloat16>::pack(a), bh = Vec16<__nv_bfloat16>::pack(b);
+    stg_stream_v4(a_hi + off, ah);
+    stg_stream_v4(b_hi + off, bh);
+    if (a_lo != nullptr) {
+      float r[8];
+      Vec16<__nv_bfloat16>::unpack(ah, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = a[e] - r[e];                     // exact in fp32
+      stg_stream_v4(a_lo + off, Vec16<__nv_bfloat16>::pack(r));
+      Vec16<__nv_bfloat16>::unpack(bh, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = b[e] - r[e];
+      stg_stream_v4(b_lo + off, Vec16<__nv_bfloat16>::pack(r));
+    }
+  }
+  if (cc * 8 < D) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      double v = acc[e];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && cc * 8 + e < D) atomicAdd(diag + cc * 8 + e, v);
+    }
+  }
+}
+
 // G (fp32 [D][D]) -> packed hi/lo planes of G and of G^T, zero padded to D_pad.
 // thread = (chunk column cc, row r); lanes run over r.  grid = (D_pad/8, D_pad/256).
 __global__ void __launch_bounds__(256) lfd_pack_g_kernel(const float* __restrict__ G, int D, int64_t D_pad,
@@ -290,12 +452,14 @@ __global__ void __launch_bounds__(256) lfd_loss_kernel(const float* __restrict__
   }
 }
 
-// sum_b dz~ and sum_b dz~*z~ per (t,d) for both tensors -> bn[2][2][TD]  (same shape as stats)
+// Small-batch path (B < 32, natural row order): sum_b dz~*z~ per (t,d) for both tensors -> bn[2][TD] fp32
+// (fp64 accumulation).  The other batch-norm moment, sum_b dz~ = sum_k (sum_b z~[b,t,k]) G[.,k] / N, vanishes
+// identically because z~ has zero batch mean, and is not computed.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) lfd_bn_reduce_kernel(const T* __restrict__ za, const T* __restrict__ zb,
                                                             const float* __restrict__ dza, const float* __restrict__ dzb,
                                                             const float* __restrict__ tables, int B, int64_t TD,
-                                                            int bsplit, double* __restrict__ bn) {
+                                                            int bsplit, float* __restrict__ bn) {
   constexpr int N = VEC ? Vec16<T>::N : 1;
   const int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (v * N >= TD) return;
@@ -310,9 +474,9 @@ __global__ void __launch_bounds__(256) lfd_bn_reduce_kernel(const T* __restrict_
   }
   const int bchunk = (B + bsplit - 1) / bsplit;
   const int b0 = blockIdx.z * bchunk, b1 = min(B, b0 + bchunk);
-  double s1[N], s2[N];
+  double s2[N];
 #pragma unroll
-  for (int e = 0; e < N; ++e) { s1[e] = 0.0; s2[e] = 0.0; }
+  for (int e = 0; e < N; ++e) s2[e] = 0.0;
   for (int b = b0; b < b1; ++b) {
     float x[N], g[N];
     const int64_t off = static_cast<int64_t>(b) * TD + v * N;
@@ -327,22 +491,21 @@ __global__ void __launch_bounds__(256) lfd_bn_reduce_kernel(const T* __restrict_
 #pragma unroll
     for (int e = 0; e < N; ++e) {
       const float zt = fmaf(x[e], sc[e], sh[e]);
-      s1[e] += static_cast<double>(g[e]);
       s2[e] += static_cast<double>(g[e]) * static_cast<double>(zt);
     }
   }
-  double* o1 = bn + static_cast<int64_t>(which) * 2 * TD + v * N;
-  double* o2 = o1 + TD;
+  float* o2 = bn + static_cast<int64_t>(which) * TD + v * N;
 #pragma unroll
   for (int e = 0; e < N; ++e) {
-    if (bsplit == 1) { o1[e] = s1[e]; o2[e] = s2[e]; }
-    else { atomicAdd(o1 + e, s1[e]); atomicAdd(o2 + e, s2[e]); }
+    if (bsplit == 1) o2[e] = static_cast<float>(s2[e]);
+    else atomicAdd(o2 + e, static_cast<float>(s2[e]));
   }
 }
 
-// dx = (dz~ - mean_b dz~ - z~ * mean_b(dz~ z~)) * rstd * upstream      (batch-norm backward)
+// dx = (dz~ - mean_b dz~ - z~ * mean_b(dz~ z~)) * rstd * upstream      (batch-norm backward; mean_b dz~ == 0)
 // Per (t,d) the expression is affine in (dz~, x):  dx = A*dz~ + Bx*x + C  with
-//   A = rstd*up,  Bx = -rstd^2 * m2 * up,  C = -(m1 + shift*m2) * rstd * up     (z~ = x*rstd + shift)
+//   A = rstd*up,  Bx = -rstd^2 * m2 * up,  C = -shift*m2 * rstd * up            (z~ = x*rstd + shift)
+// m2 = (sum over the `parts` partials bn[which][t][p][d], fixed order) / n_batch.
 // so a thread owns one 16-byte vector of the (t,d) plane, computes its coefficients once and streams
 // over the batch (same shape as the stats kernel).  grid = (ceil(TD/N/256), 2, bsplit).
 template <typename T, bool VEC>
@@ -350,9 +513,10 @@ __global__ void __launch_bounds__(256) lfd_bn_finalize_kernel(const T* __restric
                                                               const float* __restrict__ dza,
                                                               const float* __restrict__ dzb,
                                                               const float* __restrict__ tables,
-                                                              const double* __restrict__ bn, double inv_nb,
-                                                              const float* __restrict__ grad_scale, int B, int64_t TD,
-                                                              int bsplit, T* __restrict__ oa, T* __restrict__ ob) {
+                                                              const float* __restrict__ bn, int parts, int D,
+                                                              double inv_nb, const float* __restrict__ grad_scale, int B,
+                                                              int64_t TD, int bsplit, T* __restrict__ oa,
+                                                              T* __restrict__ ob) {
   constexpr int N = VEC ? Vec16<T>::N : 1;
   const int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (v * N >= TD) return;
@@ -366,11 +530,14 @@ __global__ void __launch_bounds__(256) lfd_bn_finalize_kernel(const T* __restric
   for (int e = 0; e < N; ++e) {
     const int64_t td = v * N + e;
     const float sc = tables[which * 2 * TD + td], sh = tables[which * 2 * TD + TD + td];
-    const float m1 = static_cast<float>(bn[which * 2 * TD + td] * inv_nb);
-    const float m2 = static_cast<float>(bn[which * 2 * TD + TD + td] * inv_nb);
+    const int64_t tt = td / D, dd = td - tt * D;
+    const float* bp = bn + (static_cast<int64_t>(which) * (TD / D) + tt) * parts * D + dd;
+    float acc = 0.0f;
+    for (int pp = 0; pp < parts; ++pp) acc += bp[static_cast<int64_t>(pp) * D];
+    const float m2 = static_cast<float>(static_cast<double>(acc) * inv_nb);
     cA[e] = sc * up;
     cB[e] = -sc * sc * m2 * up;
-    cC[e] = -(m1 + sh * m2) * sc * up;
+    cC[e] = -(sh * m2) * sc * up;
   }
   const int bchunk = (B + bsplit - 1) / bsplit;
   const int b0 = blockIdx.z * bchunk, b1 = min(B, b0 + bchunk);
@@ -448,7 +615,18 @@ int launch_tables(const double* sums, int64_t TD, double n_batch, float eps, flo
 }
 
 template <typename T>
-int launch_stats(const void* za, const void* zb, int dtype, int64_t B, int64_t TD, double* sums, cudaStream_t stream) {
+int launch_stats(const void* za, const void* zb, int dtype, int64_t B, int64_t Tn, int64_t D, double* sums,
+                 cudaStream_t stream) {
+  const int64_t TD = Tn * D;
+  if (vec_ok(za, zb, dtype, D) && Tn < 65536) {
+    KernelScope ks("lfd_stats_kernel", stream);
+    constexpr int N = Vec16<T>::N;
+    dim3 grid(static_cast<unsigned>((D + 64 * N - 1) / (64 * N)), static_cast<unsigned>(Tn), 2);
+    lfd_stats_rows_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb),
+                                                       static_cast<int>(B), static_cast<int>(Tn), static_cast<int>(D), sums);
+    FDDM_LAUNCH_OK();
+    return FDDM_OK;
+  }
   const bool vec = vec_ok(za, zb, dtype, TD);
   const int n = vec ? Vec16<T>::N : 1;
   const int64_t nthr = (TD + n - 1) / n;
@@ -468,13 +646,13 @@ int launch_stats(const void* za, const void* zb, int dtype, int64_t B, int64_t T
 
 template <typename T>
 int launch_bn(const void* za, const void* zb, int dtype, int64_t B, int64_t TD, const float* dza, const float* dzb,
-              const float* tables, double* bn, cudaStream_t stream) {
+              const float* tables, float* bn, cudaStream_t stream) {
   const bool vec = vec_ok(za, zb, dtype, TD) && TD % 8 == 0;
   const int n = vec ? Vec16<T>::N : 1;
   const int64_t nthr = (TD + n - 1) / n;
   const int bsplit = pick_bsplit(nthr, B);
   KernelScope ks("lfd_bn_reduce_kernel", stream);
-  if (bsplit > 1) FDDM_CUDA_OK(cudaMemsetAsync(bn, 0, sizeof(double) * 4 * TD, stream));
+  if (bsplit > 1) FDDM_CUDA_OK(cudaMemsetAsync(bn, 0, sizeof(float) * 2 * TD, stream));
   dim3 grid(static_cast<unsigned>((nthr + 255) / 256), 2, bsplit);
   if (vec)
     lfd_bn_reduce_kernel<T, true><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb), dza,
@@ -488,8 +666,8 @@ int launch_bn(const void* za, const void* zb, int dtype, int64_t B, int64_t TD, 
 
 template <typename T>
 int launch_finalize(const void* za, const void* zb, int dtype, int64_t B, int64_t TD, const float* dza,
-                    const float* dzb, const float* tables, const double* bn, double inv_nb, const float* grad_scale,
-                    void* oa, void* ob, cudaStream_t stream) {
+                    const float* dzb, const float* tables, const float* bn, int parts, int D, double inv_nb,
+                    const float* grad_scale, void* oa, void* ob, cudaStream_t stream) {
   const bool vec = vec_ok(za, zb, dtype, TD) && TD % 8 == 0 && reinterpret_cast<uintptr_t>(oa) % 16 == 0 &&
                    reinterpret_cast<uintptr_t>(ob) % 16 == 0;
   const int n = vec ? Vec16<T>::N : 1;
@@ -499,11 +677,12 @@ int launch_finalize(const void* za, const void* zb, int dtype, int64_t B, int64_
   KernelScope ks("lfd_bn_finalize_kernel", stream);
   if (vec)
     lfd_bn_finalize_kernel<T, true><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb), dza,
-                                                              dzb, tables, bn, inv_nb, grad_scale, static_cast<int>(B),
-                                                              TD, bsplit, static_cast<T*>(oa), static_cast<T*>(ob));
+                                                              dzb, tables, bn, parts, D, inv_nb, grad_scale,
+                                                              static_cast<int>(B), TD, bsplit, static_cast<T*>(oa),
+                                                              static_cast<T*>(ob));
   else
     lfd_bn_finalize_kernel<T, false><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb),
-                                                               dza, dzb, tables, bn, inv_nb, grad_scale,
+                                                               dza, dzb, tables, bn, parts, D, inv_nb, grad_scale,
                                                                static_cast<int>(B), TD, bsplit, static_cast<T*>(oa),
                                                                static_cast<T*>(ob));
   FDDM_LAUNCH_OK();
@@ -540,15 +719,29 @@ int standardise_and_pack(const void* z_a, const void* z_b, int dtype, int64_t B,
                          int terms, cudaStream_t stream) {
   float* tables = reinterpret_cast<float*>(ws + lay.off_tables);
   double* diag = reinterpret_cast<double*>(ws + lay.off_diag);
-  const int64_t TD = T * D, rows = B * T, Rp = pack_pad(rows), Dp = pack_pad(D);
+  const LfdRows rm(B, T);
+  const int64_t TD = T * D, rows = B * T, Rp = pack_pad(rm.rows_packed), Dp = pack_pad(D);
   if (int rc = launch_tables(sums, TD, n_batch_global, eps, tables, stream)) return rc;
   FDDM_CUDA_OK(cudaMemsetAsync(diag, 0, sizeof(double) * D, stream));
   __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_pack);
   const size_t pe = lay.plane_bytes / 2;
   __nv_bfloat16 *a_hi = pl, *a_lo = terms == 2 ? pl + pe : nullptr, *b_hi = pl + 2 * pe,
                 *b_lo = terms == 2 ? pl + 3 * pe : nullptr;
-  dim3 grid(static_cast<unsigned>(Dp / 64), static_cast<unsigned>(Rp / 256));
   KernelScope ks("lfd_pack_kernel", stream);
+  if (rm.tb_major) {
+    FDDM_CHECK_ARG(T < 65536, "lfd: T too large for the tb-major pack grid");
+    dim3 gtb(static_cast<unsigned>(Dp / 64), static_cast<unsigned>(T));
+#define FDDM_PACK_TB(TY)                                                                                              \
+  lfd_pack_tb_kernel<TY><<<gtb, 256, 0, stream>>>(static_cast<const TY*>(z_a), static_cast<const TY*>(z_b), tables,  \
+                                                   rm.B, rm.Bp, rm.T, static_cast<int>(D), Rp, a_hi, a_lo, b_hi, b_lo, diag)
+    if (dtype == FDDM_F32) FDDM_PACK_TB(float);
+    else if (dtype == FDDM_BF16) FDDM_PACK_TB(__nv_bfloat16);
+    else FDDM_PACK_TB(__half);
+#undef FDDM_PACK_TB
+    FDDM_LAUNCH_OK();
+    return FDDM_OK;
+  }
+  dim3 grid(static_cast<unsigned>(Dp / 64), static_cast<unsigned>(Rp / 256));
   if (dtype == FDDM_F32)
     lfd_pack_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(z_a), static_cast<const float*>(z_b),
                                                      tables, rows, static_cast<int>(T), static_cast<int>(D), Rp, a_hi,
@@ -572,7 +765,7 @@ void planes_of(uint8_t* ws, const LfdWorkspace& lay, int64_t B, int64_t T, int64
   const size_t pe = lay.plane_bytes / 2;
   A.hi = pl; A.lo = terms == 2 ? pl + pe : nullptr;
   Bo.hi = pl + 2 * pe; Bo.lo = terms == 2 ? pl + 3 * pe : nullptr;
-  A.R_pad = Bo.R_pad = pack_pad(B * T);
+  A.R_pad = Bo.R_pad = pack_pad(LfdRows(B, T).rows_packed);
   A.C_pad = Bo.C_pad = pack_pad(D);
   A.mn_is_col = Bo.mn_is_col = mn_is_col;
 }
@@ -594,7 +787,7 @@ int fddm_lfd_stats(const void* z_a, const void* z_b, int dtype, int64_t B, int64
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_common("lfd_stats", z_a, z_b, dtype, B, T, D)) return rc;
   FDDM_CHECK_ARG(sums, "lfd_stats: null sums");
-  return FDDM_DISPATCH_DT(dtype, launch_stats, z_a, z_b, dtype, B, T * D, sums, stream);
+  return FDDM_DISPATCH_DT(dtype, launch_stats, z_a, z_b, dtype, B, T, D, sums, stream);
 }
 
 int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D, const double* sums,
@@ -609,7 +802,7 @@ int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_
   const LfdWorkspace lay(B, T, D);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* partial = reinterpret_cast<float*>(ws + lay.off_splitk);
-  const int64_t rows = B * T;
+  const int64_t rows = LfdRows(B, T).rows_packed;       // contraction length incl. the zero rows of batch padding
   const int terms = (dtype == FDDM_BF16) ? 1 : 2;       // bf16 inputs: the reference's matmul operands are bf16 too
   if (int rc = standardise_and_pack(z_a, z_b, dtype, B, T, D, sums, n_batch_global, eps, ws, lay, terms, stream))
     return rc;
@@ -645,9 +838,16 @@ int fddm_lfd_loss(const float* cov, int64_t D, double n_rows_global, float lambd
   return FDDM_OK;
 }
 
+int64_t fddm_lfd_bn_parts(int64_t B, int64_t T, int64_t D) {
+  (void)D;
+  if (B <= 0 || T <= 0) return 0;
+  return fddm::LfdRows(B, T).parts();
+}
+
 int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D, const double* sums,
                       double n_batch_global, float eps, const float* G, double n_rows_global, const float* grad_scale,
-                      void* workspace, double* bn_sums, int phase, void* dz_a, void* dz_b, fddm_stream_t stream_) {
+                      void* workspace, float* bn_sums, int64_t bn_parts, int phase, void* dz_a, void* dz_b,
+                      fddm_stream_t stream_) {
   FDDM_API_RANGE();
   using namespace fddm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -656,6 +856,9 @@ int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, in
   const bool planes_valid = (phase & FDDM_LFD_PLANES_VALID) != 0;
   phase &= ~FDDM_LFD_PLANES_VALID;
   FDDM_CHECK_ARG(phase == 0 || phase == 1, "lfd_backward: phase must be 0 or 1");
+  const LfdRows rm(B, T);
+  FDDM_CHECK_ARG(phase == 0 ? bn_parts == rm.parts() : (bn_parts == rm.parts() || bn_parts == 1),
+                 "lfd_backward: bn_parts must be fddm_lfd_bn_parts(B,T,D) (phase 1 also accepts 1: partials already summed)");
   if (int rc = check_gemm_shape("lfd_backward", z_a, z_b, D)) return rc;
   const LfdWorkspace lay(B, T, D);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -684,6 +887,13 @@ int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, in
     planes_of(ws, lay, B, T, D, 2, 0, Za, Zb);
     Gk.hi = gp; Gk.lo = gp + ge; Gk.R_pad = Dp; Gk.C_pad = Dp; Gk.mn_is_col = 0;            // B(n=j, k) = G[j][k]
     Gt = Gk; Gt.hi = gp + 2 * ge; Gt.lo = gp + 3 * ge;                                      // B(n=k, j) = G^T[k][j]
+    if (rm.tb_major) {
+      // persistent contraction whose epilogue also emits the batch sums of dz~ * z~ as [T][Bp/32][D] partials
+      float* bn_a = bn_sums;
+      float* bn_b = bn_sums + static_cast<int64_t>(T) * rm.parts() * D;
+      if (int rc = umma_bwd_gemm(Zb, Gk, Za, rm, D, alpha, dza, bn_a, stream)) return rc;
+      return umma_bwd_gemm(Za, Gt, Zb, rm, D, alpha, dzb, bn_b, stream);
+    }
     // dza~[r][j] = (1/N) sum_k zb~[r][k] G[j][k]          (oracle: B2 @ G.T / N)
     if (int rc = umma_gemm(Zb, Gk, rows, D, D, 1, 2, alpha, dza, D, 0, stream)) return rc;
     // dzb~[r][k] = (1/N) sum_j za~[r][j] G[j][k]          (oracle: A2 @ G / N)
@@ -691,7 +901,8 @@ int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, in
     return FDDM_DISPATCH_DT(dtype, launch_bn, z_a, z_b, dtype, B, TD, dza, dzb, tables, bn_sums, stream);
   }
   return FDDM_DISPATCH_DT(dtype, launch_finalize, z_a, z_b, dtype, B, TD, dza, dzb, tables, bn_sums,
-                          1.0 / n_batch_global, grad_scale, dz_a, dz_b, stream);
+                          static_cast<int>(bn_parts), static_cast<int>(D), 1.0 / n_batch_global, grad_scale, dz_a, dz_b,
+                          stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,272 @@
+// lfd_umma_bwd.cu -- the backward contractions of L_fd as ONE persistent tcgen05 kernel per gradient:
+//
+//   dz~[r][n]       = alpha * sum_k Z(r, k) * G(n, k)          Z: z~ planes of the other tensor, G: dloss/dC (or G^T)
+//   partial[g][n]   = sum_{r in 32-row group g} dz~[r][n] * Zs(r, n)      Zs: z~ planes of the tensor dz~ belongs to
+//
+// (reference: autograd of losses/fddm_losses.py:48-57 through _standardize, losses:18-26.)
+//
+// What changed against the one-tile-per-CTA kernel it replaces (profiles/r01b_umma_bwd_ncu_full_selected.csv:
+// tensor pipe 25 % of elapsed, 2.6 waves, a 131 KB epilogue and the TMEM-alloc prologue exposed around a
+// 24-k-block main loop; then a separate pass over dz~ and z for the batch-norm sums):
+//   * persistent CTAs (one per SM) walk the (m-tile, n-tile) list; the operand ring runs on across tiles;
+//   * TWO 256-column TMEM accumulators alternate, so the epilogue of tile i (TMEM -> registers -> global) runs
+//     under the main loop of tile i+1;
+//   * rows are tb-major (lfd_common.cuh): the 32 rows an epilogue warp owns share one position t, so the batch
+//     sums of dz~ * z~ are a 32-lane butterfly over registers the epilogue already holds -- the batch-norm
+//     reduction pass over dz~ and z (lfd_bn_reduce_kernel) disappears; z~ comes from the packed planes with
+//     fully coalesced 16-byte loads.
+//
+// Warp roles as in lfd_umma.cu: warp 0 TMA producer, warp 1 MMA issuer (one lane) + TMEM owner, warps 2..5
+// epilogue (TMEM lane quarter = warp id % 4).
+#include <algorithm>
+
+#include "umma_common.cuh"
+
+namespace fddm {
+namespace {
+using namespace umma;
+
+constexpr int kBwdBN = 256;
+constexpr int kBwdStages = 4;
+constexpr uint32_t kBwdStageBytes = 2 * (kTileA + kTileB);          // hi + lo planes of A and B: 48 KB
+
+struct BwdParams {
+  const __nv_bfloat16 *z_hi, *z_lo;      // A operand  [D_pad/8][R_pad][8]
+  const __nv_bfloat16 *g_hi, *g_lo;      // B operand  [D_pad/8][D_pad][8]
+  const __nv_bfloat16 *s_hi, *s_lo;      // statistics operand, same layout as z
+  int64_t R_pad, D_pad;
+  int D;                                 // N = K = D
+  int tiles_n, num_kb, total;
+  int Bn, Bp, Tn;
+  float alpha;
+  float* dz;                             // [B][T][D] fp32
+  float* partial;                        // [T * Bp/32][D] fp32
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t s_full[kBwdStages], s_empty[kBwdStages], s_acc_full[2], s_acc_empty[2];
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kBwdStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_acc_full[b], 1);
+      mbar_init(&s_acc_empty[b], kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {                                   // the MMA warp owns the TMEM allocation (all 512 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(static_cast<uint32_t>(2 * kBwdBN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ===== producer: 16 bulk copies per stage, one per lane =====
+    // lane -> (operand, plane, chunk column of the k-block)
+    const int op = (lane >> 3) & 1, pl = (lane >> 2) & 1, c = lane & 3;
+    const __nv_bfloat16* plane = op == 0 ? (pl == 0 ? p.z_hi : p.z_lo) : (pl == 0 ? p.g_hi : p.g_lo);
+    const int64_t plane_rows = op == 0 ? p.R_pad : p.D_pad;
+    const uint32_t bytes = op == 0 ? kBM * 16u : kBwdBN * 16u;
+    const uint32_t dst_off = (op == 0 ? pl * kTileA : 2 * kTileA + pl * kTileB) + static_cast<uint32_t>(c) * bytes;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+      const int64_t m0 = static_cast<int64_t>(w / p.tiles_n) * kBM, n0 = static_cast<int64_t>(w % p.tiles_n) * kBwdBN;
+      const int64_t mn0 = op == 0 ? m0 : n0;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = static_cast<int>(it % kBwdStages);
+        const uint32_t round = it / kBwdStages;
+        if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1);
+        if (lane == 0) mbar_arrive_expect_tx(&s_full[s], kBwdStageBytes);
+        __syncwarp();
+        if (lane < 16) {
+          const int64_t cc = static_cast<int64_t>(kb) * (kBK / 8) + c;
+          tma_load_1d(smem + static_cast<size_t>(s) * kBwdStageBytes + dst_off, plane + (cc * plane_rows + mn0) * 8, bytes,
+                      &s_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(0, 0, kBwdBN);
+      constexpr uint32_t csA = kBM * 16u, csB = kBwdBN * 16u;       // bytes between chunk columns (K-major tiles)
+      uint32_t it = 0, local = 0;
+      for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++local) {
+        const uint32_t buf = local & 1, use = local >> 1;
+        if (use > 0) {                                               // the epilogue must have drained this accumulator
+          mbar_wait(&s_acc_empty[buf], (use - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t tmem_d = tmem_base + buf * kBwdBN;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = static_cast<int>(it % kBwdStages);
+          const uint32_t round = it / kBwdStages;
+          mbar_wait(&s_full[s], round & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * kBwdStageBytes);
+          const uint32_t a_hi = st, a_lo = st + kTileA, b_hi = st + 2 * kTileA, b_lo = b_hi + kTileB;
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {                     // hi*hi, hi*lo, lo*hi
+            const uint32_t a_base = (term == 2) ? a_lo : a_hi;
+            const uint32_t b_base = (term == 1) ? b_lo : b_hi;
+#pragma unroll
+            for (int ks = 0; ks < kBK / 16; ++ks) {
+              umma_bf16(tmem_d, make_smem_desc(a_base + ks * 2u * csA, csA, 128u),
+                        make_smem_desc(b_base + ks * 2u * csB, csB, 128u), idesc, accum);
+              accum = 1;
+            }
+          }
+          umma_commit(&s_empty[s]);                                  // stage reusable once these MMAs have read it
+        }
+        umma_commit(&s_acc_full[buf]);                               // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;                                          // TMEM lane quarter of this warp
+    uint32_t local = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++local) {
+      const int64_t m0 = static_cast<int64_t>(w / p.tiles_n) * kBM;
+      const int n0 = (w % p.tiles_n) * kBwdBN;
+      const uint32_t buf = local & 1, use = local >> 1;
+      const int64_t r0 = m0 + q * 32, r = r0 + lane;                 // packed rows of this warp / lane
+      const int t = static_cast<int>(r0 / p.Bp), b = static_cast<int>(r - static_cast<int64_t>(t) * p.Bp);
+      const bool t_ok = t < p.Tn, row_ok = t_ok && b < p.Bn;
+      float* orow = p.dz + (static_cast<int64_t>(b) * p.Tn + t) * p.D;
+      float* prow = p.partial + (r0 >> 5) * p.D;
+      mbar_wait(&s_acc_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * kBwdBN + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c = 0; c < kBwdBN && n0 + c < p.D; c += 16) {
+        // z~ of the statistics tensor for (r, n0+c .. +15): two chunk columns, hi + lo, 16-byte loads that are
+        // contiguous across the 32 lanes (issued before the TMEM load so their latency overlaps it)
+        const int64_t cc = (n0 + c) >> 3;
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(p.s_hi + (cc * p.R_pad + r) * 8));
+        const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(p.s_lo + (cc * p.R_pad + r) * 8));
+        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(p.s_hi + ((cc + 1) * p.R_pad + r) * 8));
+        const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(p.s_lo + ((cc + 1) * p.R_pad + r) * 8));
+        float v[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+        if (row_ok) {                                                // D is a multiple of 8: whole float4s
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            if (n0 + c + 4 * h < p.D)
+              *reinterpret_cast<float4*>(orow + n0 + c + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+        }
+        float z[16], zl[8];
+        unpack_bf16x8(h0, z); unpack_bf16x8(l0, zl);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] += zl[i];
+        unpack_bf16x8(h1, z + 8); unpack_bf16x8(l1, zl);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[8 + i] += zl[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= z[i];                   // padded rows: z~ = 0 and dz~ = 0
+        // column sums over the warp's 32 rows: transposing butterfly, 16 -> 8 -> 4 -> 2 -> 1 values per lane
+        float y8[8], y4[4], y2[2], y1;
+        {
+          const bool up = (lane & 16) != 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float keep = up ? v[8 + i] : v[i], send = up ? v[i] : v[8 + i];
+            y8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+        }
+        {
+          const bool up = (lane & 8) != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float keep = up ? y8[4 + i] : y8[i], send = up ? y8[i] : y8[4 + i];
+            y4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+        }
+        {
+          const bool up = (lane & 4) != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float keep = up ? y4[2 + i] : y4[i], send = up ? y4[i] : y4[2 + i];
+            y2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+        {
+          const bool up = (lane & 2) != 0;
+          const float keep = up ? y2[1] : y2[0], send = up ? y2[0] : y2[1];
+          y1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
+        const int col = n0 + c + (lane >> 1);                        // lane bits (4,3,2,1) = column bits (3,2,1,0)
+        if (t_ok && (lane & 1) == 0 && col < p.D) prow[col] = y1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(2 * kBwdBN))
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+int umma_bwd_gemm(const PackedOperand& Z, const PackedOperand& G, const PackedOperand& Zs, const LfdRows& rows, int64_t D,
+                  float alpha, float* dz, float* partial, cudaStream_t stream) {
+  FDDM_CHECK_ARG(rows.tb_major, "umma_bwd_gemm: needs tb-major planes (B >= 32)");
+  FDDM_CHECK_ARG(Z.hi && Z.lo && G.hi && G.lo && Zs.hi && Zs.lo && dz && partial, "umma_bwd_gemm: null pointer");
+  FDDM_CHECK_ARG(D > 0 && D % 8 == 0, "umma_bwd_gemm: D must be a positive multiple of 8");
+  FDDM_CHECK_ARG(Z.R_pad % kPackPad == 0 && Z.C_pad % kPackPad == 0 && G.R_pad == Z.C_pad && G.C_pad == Z.C_pad &&
+                     Zs.R_pad == Z.R_pad && Zs.C_pad == Z.C_pad && Z.R_pad >= rows.rows_packed && Z.C_pad >= D,
+                 "umma_bwd_gemm: packed operand padding");
+  FDDM_CHECK_ARG(reinterpret_cast<uintptr_t>(dz) % 16 == 0, "umma_bwd_gemm: dz must be 16-byte aligned");
+  BwdParams p;
+  p.z_hi = Z.hi; p.z_lo = Z.lo; p.g_hi = G.hi; p.g_lo = G.lo; p.s_hi = Zs.hi; p.s_lo = Zs.lo;
+  p.R_pad = Z.R_pad; p.D_pad = Z.C_pad;
+  p.D = static_cast<int>(D);
+  p.tiles_n = static_cast<int>((D + kBwdBN - 1) / kBwdBN);
+  p.num_kb = static_cast<int>((D + kBK - 1) / kBK);
+  const int64_t tiles_m = (rows.rows_packed + kBM - 1) / kBM;        // R_pad is a multiple of 256 >= rows_packed
+  const int64_t total = tiles_m * p.tiles_n;
+  FDDM_CHECK_ARG(total < (1ll << 31), "umma_bwd_gemm: too many tiles");
+  p.total = static_cast<int>(total);
+  p.Bn = rows.B; p.Bp = rows.Bp; p.Tn = rows.T;
+  p.alpha = alpha; p.dz = dz; p.partial = partial;
+  const size_t smem = static_cast<size_t>(kBwdStages) * kBwdStageBytes;
+  FDDM_CUDA_OK(cudaFuncSetAttribute(umma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int grid = static_cast<int>(std::min<int64_t>(total, num_sms()));
+  KernelScope ks("umma_bwd_persistent (z~ G + bn partials)", stream);
+  umma_bwd_kernel<<<grid, kThreads, smem, stream>>>(p);
+  FDDM_LAUNCH_OK();
+  return FDDM_OK;
+}
+
+}  // namespace fddm

@@ -59,8 +59,9 @@ SIGNATURES = {
     "fddm_lfd_stats": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp]),
     "fddm_lfd_xcov": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _f64, _f32, _vp, _vp, _vp]),
     "fddm_lfd_loss": (_i32, [_vp, _i64, _f64, _f32, _vp, _vp, _vp, _vp]),
-    "fddm_lfd_backward": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _f64, _f32, _vp, _f64, _vp, _vp, _vp, _i32,
-                                 _vp, _vp, _vp]),
+    "fddm_lfd_bn_parts": (_i64, [_i64, _i64, _i64]),
+    "fddm_lfd_backward": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _f64, _f32, _vp, _f64, _vp, _vp, _vp, _i64,
+                                 _i32, _vp, _vp, _vp]),
 }
 MISSING = []                               # symbols of the ABI the loaded library does not export
 for _name, (_res, _args) in SIGNATURES.items():

@@ -81,48 +81,42 @@ class _LfdLossFn(torch.autograd.Function):
         L.check(L.lib.fddm_lfd_loss(op.cov.data_ptr(), D, float(B * T * op.world), op.lam, op.ws.data_ptr(),
                                     loss.data_ptr(), G.data_ptr(), L.stream_ptr(dev)), "lfd_loss")
         ctx.save_for_backward(z_a, z_b, op.sums, G, op.ws)
-        ctx.meta = (B, T, D, op.dt, op.world, op.eps, op.group, op.private_ws, op.bn_full)
+        ctx.meta = (B, T, D, op.dt, op.world, op.eps, op.group, op.private_ws)
         return loss.to(z_a.dtype)                              # the reference's result has the input dtype
 
     @staticmethod
     def backward(ctx, grad_out):
         z_a, z_b, sums, G, ws = ctx.saved_tensors
-        B, T, D, dt, world, eps, group, private_ws, bn_full = ctx.meta
+        B, T, D, dt, world, eps, group, private_ws = ctx.meta
         dev = z_a.device
         st = L.stream_ptr(dev)
-        bn = torch.empty(4 * T * D, dtype=torch.float64, device=dev)
+        parts = int(L.lib.fddm_lfd_bn_parts(B, T, D))
+        bn = torch.empty(2 * T * parts * D, dtype=torch.float32, device=dev)
         dz_a = torch.empty_like(z_a)
         dz_b = torch.empty_like(z_b)
         g = grad_out.to(torch.float32).contiguous()
         args = (z_a.data_ptr(), z_b.data_ptr(), dt, B, T, D, sums.data_ptr(), float(B * world), eps, G.data_ptr(),
-                float(B * T * world), g.data_ptr(), ws.data_ptr(), bn.data_ptr())
+                float(B * T * world), g.data_ptr(), ws.data_ptr())
         # the forward's packed operand planes / tables are reused when the workspace was private to this call
         phase0 = 0 | (L.LFD_PLANES_VALID if private_ws else 0)
-        L.check(L.lib.fddm_lfd_backward(*args, phase0, dz_a.data_ptr(), dz_b.data_ptr(), st), "lfd_backward[0]")
-        if group is not None and bn_full:
-            torch.distributed.all_reduce(bn, op=torch.distributed.ReduceOp.SUM, group=group)   # fp64 [2][2][TD]
-        elif group is not None:
-            # Only sum_b dz~*z~ crosses ranks, in fp32 (1/4 of the bytes of the fp64 block).  The other moment,
-            # sum_b dz~ = sum_k (sum_b z~[b,t,k]) G[.,k] / N, is identically zero over the GLOBAL batch because
-            # z~ has zero global batch mean (a rank's partial sum is NOT zero), so it is set to zero instead
-            # of being reduced: the dropped term is rounding noise (~1e-7 relative).
-            v = bn.view(2, 2, T * D)
-            m2 = v[:, 1, :].float()
-            torch.distributed.all_reduce(m2, op=torch.distributed.ReduceOp.SUM, group=group)
-            v[:, 1, :].copy_(m2)
-            v[:, 0, :].zero_()
-        L.check(L.lib.fddm_lfd_backward(*args, 1, dz_a.data_ptr(), dz_b.data_ptr(), st), "lfd_backward[1]")
+        L.check(L.lib.fddm_lfd_backward(*args, bn.data_ptr(), parts, phase0, dz_a.data_ptr(), dz_b.data_ptr(), st),
+                "lfd_backward[0]")
+        if group is not None:
+            # Only sum_b dz~*z~ crosses ranks, in fp32: [2][T][D].  (The other batch-norm moment, sum_b dz~ =
+            # sum_k (sum_b z~[b,t,k]) G[.,k] / N, is identically zero over the GLOBAL batch because z~ has zero
+            # global batch mean; the library never computes it.)
+            if parts > 1:
+                bn = bn.view(2 * T, parts, D).sum(dim=1).contiguous()
+                parts = 1
+            torch.distributed.all_reduce(bn, op=torch.distributed.ReduceOp.SUM, group=group)
+        L.check(L.lib.fddm_lfd_backward(*args, bn.data_ptr(), parts, 1, dz_a.data_ptr(), dz_b.data_ptr(), st),
+                "lfd_backward[1]")
         return dz_a, dz_b, None
 
 
 class LfdPipeline:
     def __init__(self, z_a: torch.Tensor, z_b: torch.Tensor, lambda_offdiag: float = 5.0e-3, eps: float = 1e-5, *,
-                 group=None, overlap: bool = False, bn_allreduce: str = "moment"):
-        """`bn_allreduce`: what the sharded backward exchanges -- "moment" (default): only sum_b dz~*z~ in fp32,
-        the other batch-norm moment being zero over the global batch; "full": both moments in fp64."""
-        if bn_allreduce not in ("moment", "full"):
-            raise ValueError("bn_allreduce must be 'moment' or 'full'")
-        self.bn_full = bn_allreduce == "full"
+                 group=None, overlap: bool = False):
         if z_a.dim() != 3:
             raise ValueError(f"z_a must be (B, T, D), got shape {tuple(z_a.shape)}")
         B, T, D = z_a.shape

@@ -175,10 +175,14 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
  *   3. fddm_lfd_loss      C = cov / n_rows_global; loss = sum_j (1-C_jj)^2 + lambda sum_{j!=k} C_jk^2;
  *                         G[D,D] = dloss/dC                                               losses:51-57
  *   4. fddm_lfd_backward  phase 0: dza~ = zb~ G^T / N, dzb~ = za~ G / N (two tcgen05 contractions into
- *                         the workspace) and bn_sums = fp64 [2][2][T*D]: sum_b dz~, sum_b dz~ z~
- *                         -> all-reduce bn_sums
- *                         phase 1: dz = (dz~ - mean_b dz~ - z~ mean_b(dz~ z~)) / std * (*grad_scale),
- *                         written in the input dtype.
+ *                         the workspace) and bn_sums = fp32 [2 tensors][T][P][D], P = fddm_lfd_bn_parts(B,T,D):
+ *                         partial batch sums of dz~ z~ per (t, d) (for B >= 32 they come out of the
+ *                         contraction's epilogue, one partial per 32 batch rows; P = 1 for B < 32).
+ *                         The other batch-norm moment, sum_b dz~, is identically zero (z~ has zero batch
+ *                         mean) and is not computed.
+ *                         -> sum the P partials and all-reduce [2][T][D] when the batch is sharded
+ *                         phase 1: dz = (dz~ - z~ mean_b(dz~ z~)) / std * (*grad_scale), written in the
+ *                         input dtype; bn_parts = P, or 1 when the caller passes already-summed sums.
  *
  * workspace: fddm_lfd_workspace_bytes(B,T,D) bytes whose first 256 bytes are zero-initialised ONCE by
  * the caller (self-resetting counters); the rest is scratch (tables, split-K partials, dz~).
@@ -193,10 +197,12 @@ int fddm_lfd_xcov(const void* z_a, const void* z_b, int dtype, int64_t B, int64_
                   float* cov /* [D,D] */, fddm_stream_t stream);
 int fddm_lfd_loss(const float* cov, int64_t D, double n_rows_global, float lambda_offdiag,
                   void* workspace, float* loss_out, float* G /* [D,D] */, fddm_stream_t stream);
+int64_t fddm_lfd_bn_parts(int64_t B, int64_t T, int64_t D);
 int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, int64_t T, int64_t D,
                       const double* sums, double n_batch_global, float eps, const float* G,
                       double n_rows_global, const float* grad_scale, void* workspace,
-                      double* bn_sums, int phase, void* dz_a, void* dz_b, fddm_stream_t stream);
+                      float* bn_sums, int64_t bn_parts, int phase, void* dz_a, void* dz_b,
+                      fddm_stream_t stream);
 
 #ifdef __cplusplus
 }

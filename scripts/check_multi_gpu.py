@@ -2,7 +2,8 @@
 """Multi-GPU correctness check (launch with torchrun, one rank per GPU, NCCL): the batch-sharded
 kl_term / lfd_loss (values AND gradients) equal the single-process evaluation on the whole batch.
 The check itself is bench.shard_check (bench.py runs it before timing whenever WORLD_SIZE > 1);
-this script runs it for both backward exchange variants and exits non-zero on failure."""
+this script runs it for per-rank batches 8 (small-batch L_fd path), 32 and 40 (tb-major path, with batch
+padding) and exits non-zero on failure."""
 import json
 import os
 import sys
@@ -22,8 +23,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for variant in ("moment", "full"):
-        res = bench.shard_check(fb, dev, dist.group.WORLD, world, rank, bn_allreduce=variant)
+    for per_rank_b in (8, 32, 40):
+        res = bench.shard_check(fb, dev, dist.group.WORLD, world, rank, per_rank_b=per_rank_b)
         ok = ok and res["ok"]
         if rank == 0:
             print("multi-gpu check", "OK" if res["ok"] else "FAILED", "world", world, json.dumps(res), flush=True)

@@ -447,7 +447,10 @@ def test_lfd_golden(fb, golden, tag):
 
 @pytest.mark.parametrize("io", ["f32", "bf16", "f16"])
 @pytest.mark.parametrize("B,T,D,rho", [(32, 128, 768, 0.0), (32, 128, 768, 0.9), (16, 37, 256, 0.9), (4, 130, 264, 0.5),
-                                       (8, 5, 16, 0.9)])
+                                       (8, 5, 16, 0.9),
+                                       # B >= 32: tb-major planes, persistent backward contraction with the batch sums
+                                       # in its epilogue; batch padding (33 -> 64, 96, 130 -> 160), ragged T and D
+                                       (33, 7, 40, 0.9), (64, 16, 264, 0.5), (96, 5, 768, 0.9), (130, 3, 256, 0.0)])
 def test_lfd_vs_oracle(fb, io, B, T, D, rho):
     rng = np.random.default_rng(D + T)
     za = (rng.normal(size=(B, T, D)) * 1.7 + 0.3).astype(np.float32)

@@ -97,7 +97,7 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
   // (max, sum) pairs gives the row max m and S = sum_k exp(z_k - m).  The registers keep exp(z_k - m_t);
   // the per-thread factor f_t = exp(m_t - m) is folded into the coefficients of the later passes.
   float m_t = kNegInf;
-  row.for_each([&](int, float& x) { m_t = fmaxf(m_t, x); });
+  row.for_each_ro([&](int, float x) { m_t = fmaxf(m_t, x); });
   const float nm_t = -m_t * kLog2e;
   float s_t = 0.0f;
   row.for_each([&](int, float& x) {
@@ -199,12 +199,17 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
         G += g_sp[i] * xh_sp[i];
       }
     }
-    // pass 4: gradient  e_k * (A/y_k + Bc) = e_k * (Ar/r_k + Bc), generic entries from registers ...
+    // pass 4: gradient  e_k * (A/y_k + Bc) = e_k * (Ar/r_k + Bc), generic entries from the row; the <= 2 special
+    // entries are replaced by their exact values by whichever thread owns their group (no barrier, no second
+    // store to the same address)
     const float Ar = -wscale * inv_S * cg * iq * f_t;   // e_k here is exp(z_k - m_t): fold f_t in
     const float Bc = -wscale * inv_S * G * f_t;
-    row.store4(
+    const float gx_xt = wscale * xh_sp[0] * (g_sp[0] - G);
+    const float gx_x0 = same ? 0.0f : wscale * xh_sp[1] * (g_sp[1] - G);
+    const int q_xt = xt & ~3, q_x0 = same ? -4 : (x0 & ~3);
+    row.store4k(
         grad_row,
-        [&](const float* e, float* o) {
+        [&](int k0, const float* e, float* o) {
           const float r0 = fmaf(c1r, e[0], c0r), r1 = fmaf(c1r, e[1], c0r);
           const float r2 = fmaf(c1r, e[2], c0r), r3 = fmaf(c1r, e[3], c0r);
           const float p01 = r0 * r1, p23 = r2 * r3;
@@ -214,14 +219,14 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
           o[1] = e[1] * fmaf(Ar, r0 * h01, Bc);
           o[2] = e[2] * fmaf(Ar, r3 * h23, Bc);
           o[3] = e[3] * fmaf(Ar, r2 * h23, Bc);
+          if (k0 == q_xt) o[xt & 3] = gx_xt;
+          if (k0 == q_x0) o[x0 & 3] = gx_x0;
         },
-        [&](float e) { return e * fmaf(Ar, rcp_approx(fmaf(c1r, e, c0r)), Bc); });
-    // ... then the special entries overwritten with their exact values
-    consumer_sync<NT>();
-    if (threadIdx.x == 0) {
-      Vec16<T>::store1(grad_row + xt, wscale * xh_sp[0] * (g_sp[0] - G));
-      if (!same) Vec16<T>::store1(grad_row + x0, wscale * xh_sp[1] * (g_sp[1] - G));
-    }
+        [&](int k, float e) {
+          if (k == xt) return gx_xt;
+          if (k == x0) return gx_x0;
+          return e * fmaf(Ar, rcp_approx(fmaf(c1r, e, c0r)), Bc);
+        });
   }
   return kl;
 }

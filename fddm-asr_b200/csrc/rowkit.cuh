@@ -56,6 +56,11 @@ struct RegRow {
       }
     }
   }
+  // read-only visit f(k, x) (same as for_each here; rows that live in shared memory skip the write-back)
+  template <class F>
+  __device__ __forceinline__ void for_each_ro(F&& f) {
+    for_each([&](int k, float& x) { f(k, x); });
+  }
   // which thread owns element k / how many elements this thread owns
   __device__ __forceinline__ int owner_of(int k) const { return (k / N) % NT; }
   __device__ __forceinline__ int n_owned() const {
@@ -88,6 +93,20 @@ struct RegRow {
       }
     }
   }
+  // same, g4(k0, x4, o4) also gets the index of the group's first element
+  template <class G4, class G1>
+  __device__ __forceinline__ void store4k(T* dst, G4&& g4, G1&&) {
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int vi = j * NT + tid;
+      if (vi < nvec) {
+        float o[N];
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) g4(vi * N + 4 * q, &v[j * N + 4 * q], &o[4 * q]);
+        stg_stream_v4(reinterpret_cast<uint4*>(dst) + vi, Vec16<T>::pack(o));
+      }
+    }
+  }
   // dst[k] = g(k, x) for the whole row, 128-bit streaming stores
   template <class G>
   __device__ __forceinline__ void store(T* dst, G&& g) {
@@ -100,6 +119,59 @@ struct RegRow {
         for (int e = 0; e < N; ++e) o[e] = g(vi * N + e, v[j * N + e]);
         stg_stream_v4(reinterpret_cast<uint4*>(dst) + vi, Vec16<T>::pack(o));
       }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// StageRow: an fp32 row that STAYS in the shared-memory stage the TMA copy filled (V % 4 == 0, 16-byte
+// aligned); every pass streams over it with 128-bit LDS, pass results that must persist (exp) are written
+// back in place.  Thread `tid` owns the vectors tid, tid+NT, ...  No registers hold the row, so the
+// kernels built on it fit 4-6 CTAs per SM: rows in flight are limited by shared memory, not registers.
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+struct StageRow {
+  static constexpr int N = 4;
+  float4* s4;
+  int nvec, tid;
+  __device__ __forceinline__ void bind(void* stage, int V, int tid_) {
+    s4 = reinterpret_cast<float4*>(stage); nvec = V / 4; tid = tid_;
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_ro(F&& f) {
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      const float4 v = s4[vi];
+      f(vi * 4, v.x); f(vi * 4 + 1, v.y); f(vi * 4 + 2, v.z); f(vi * 4 + 3, v.w);
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each(F&& f) {          // read-modify-write
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      float4 v = s4[vi];
+      f(vi * 4, v.x); f(vi * 4 + 1, v.y); f(vi * 4 + 2, v.z); f(vi * 4 + 3, v.w);
+      s4[vi] = v;
+    }
+  }
+  template <class F4, class F1>
+  __device__ __forceinline__ void for_each4(F4&& f4, F1&&) {
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      const float4 v = s4[vi];
+      float e[4] = {v.x, v.y, v.z, v.w};
+      f4(e);
+    }
+  }
+  template <class G4, class G1>
+  __device__ __forceinline__ void store4k(float* dst, G4&& g4, G1&&) {
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      const float4 v = s4[vi];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      float o[4];
+      g4(vi * 4, e, o);
+      stg_stream_v4(reinterpret_cast<uint4*>(dst) + vi, Vec16<float>::pack(o));
     }
   }
 };
@@ -128,6 +200,10 @@ struct SmemRow {
       for (int e = 0; e < 4; ++e) f(k + e, r[k + e]);
     }
     for (int k = V4 + tid; k < V; k += NT) f(k, r[k]);
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_ro(F&& f) {
+    for_each([&](int k, float& x) { f(k, x); });
   }
   template <class G>
   __device__ __forceinline__ void store(T* dst, G&& g) {
@@ -164,6 +240,18 @@ struct SmemRow {
       for (int e = 0; e < 4; ++e) Vec16<T>::store1(dst + k + e, o[e]);
     }
     for (int k = V4 + tid; k < V; k += NT) Vec16<T>::store1(dst + k, g1(r[k]));
+  }
+  // index-aware variants: g4(k0, x4, o4), g1(k, x)
+  template <class G4, class G1>
+  __device__ __forceinline__ void store4k(T* dst, G4&& g4, G1&& g1) {
+    const int V4 = V & ~3;
+    for (int k = 4 * tid; k < V4; k += 4 * NT) {
+      float o[4];
+      g4(k, &r[k], o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Vec16<T>::store1(dst + k + e, o[e]);
+    }
+    for (int k = V4 + tid; k < V; k += NT) Vec16<T>::store1(dst + k, g1(k, r[k]));
   }
 };
 

@@ -16,10 +16,8 @@
 // so the per-element work is one exp, one log (and one reciprocal for the gradient); the <=2 special
 // entries are patched with their exact values.
 #include <math.h>
-#include <stdlib.h>
 
 #include <algorithm>
-#include <type_traits>
 
 #include "rowkit.cuh"
 
@@ -203,17 +201,12 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
         G += g_sp[i] * xh_sp[i];
       }
     }
-    // pass 4: gradient  e_k * (A/y_k + Bc) = e_k * (Ar/r_k + Bc), generic entries from the row; the <= 2 special
-    // entries are replaced by their exact values by whichever thread owns their group (no barrier, no second
-    // store to the same address)
+    // pass 4: gradient  e_k * (A/y_k + Bc) = e_k * (Ar/r_k + Bc), generic entries from the row ...
     const float Ar = -wscale * inv_S * cg * iq * f_t;   // e_k here is exp(z_k - m_t): fold f_t in
     const float Bc = -wscale * inv_S * G * f_t;
-    const float gx_xt = wscale * xh_sp[0] * (g_sp[0] - G);
-    const float gx_x0 = same ? 0.0f : wscale * xh_sp[1] * (g_sp[1] - G);
-    const int q_xt = xt & ~3, q_x0 = same ? -4 : (x0 & ~3);
-    row.store4k(
+    row.store4(
         grad_row,
-        [&](int k0, const float* e, float* o) {
+        [&](const float* e, float* o) {
           const float r0 = fmaf(c1r, e[0], c0r), r1 = fmaf(c1r, e[1], c0r);
           const float r2 = fmaf(c1r, e[2], c0r), r3 = fmaf(c1r, e[3], c0r);
           const float p01 = r0 * r1, p23 = r2 * r3;
@@ -223,14 +216,12 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
           o[1] = e[1] * fmaf(Ar, r0 * h01, Bc);
           o[2] = e[2] * fmaf(Ar, r3 * h23, Bc);
           o[3] = e[3] * fmaf(Ar, r2 * h23, Bc);
-          if (k0 == q_xt) o[xt & 3] = gx_xt;
-          if (k0 == q_x0) o[x0 & 3] = gx_x0;
         },
-        [&](int k, float e) {
-          if (k == xt) return gx_xt;
-          if (k == x0) return gx_x0;
-          return e * fmaf(Ar, rcp_approx(fmaf(c1r, e, c0r)), Bc);
-        });
+        [&](float e) { return e * fmaf(Ar, rcp_approx(fmaf(c1r, e, c0r)), Bc); });
+    // ... then the <= 2 special entries are overwritten with their exact values by the thread that owns them:
+    // same thread, same address, program order -- no barrier needed
+    if (row.owner_of(xt) == row.tid) Vec16<T>::store1(grad_row + xt, wscale * xh_sp[0] * (g_sp[0] - G));
+    if (!same && row.owner_of(x0) == row.tid) Vec16<T>::store1(grad_row + x0, wscale * xh_sp[1] * (g_sp[1] - G));
   }
   return kl;
 }
@@ -385,108 +376,6 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
 }
 
 // ------------------------------------------------------------------------------------------------
-// streamed path (fp32 logits): the row stays in the shared-memory stage the TMA copy filled and every pass
-// streams over it (StageRow); exp(z - m_t) is written back in place.  ~60 registers per thread instead of
-// ~100, so 4-6 CTAs are resident per SM: what bounded the register-resident kernel (0.72-0.79 of HBM peak at
-// 2 CTAs/SM, 58 % issue utilisation) was the per-row latency chain (two block reductions) with only two rows
-// in flight per SM.  The stage is handed back only when the row is finished; the producer reads the two
-// special logits (z[x_t], z[x_0]) from global memory under the copy's latency and passes them in the
-// stage's metadata, so no consumer needs them from the stage before it is overwritten.
-// ------------------------------------------------------------------------------------------------
-template <int NT, bool BWD, int CTAS>
-__global__ void __launch_bounds__(NT + 32, CTAS)
-kl_rows_streamed_kernel(const KlParams p, const int nstages, const uint32_t stage_bytes) {
-  extern __shared__ __align__(128) uint8_t dyn_smem[];
-  __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages];
-  __shared__ RingMeta s_meta[kMaxStages];
-  __shared__ float s_red[kRedFloats];
-  __shared__ int s_flag;
-
-  Ring ring;
-  ring.stages = dyn_smem;
-  ring.stage_bytes = stage_bytes;
-  ring.nstages = nstages;
-  ring.full = s_full;
-  ring.empty = s_empty;
-  ring.meta = s_meta;
-  ring_init<NT>(ring);
-
-  const int tid = threadIdx.x;
-  const uint32_t row_bytes = static_cast<uint32_t>(p.V) * sizeof(float);
-  const float* logits = static_cast<const float*>(p.logits);
-
-  if (tid >= NT) {
-    // ===== producer warp =====
-    const int lane = tid - NT;
-    int s = 0;
-    uint32_t round = 0;
-    for (;;) {
-      if (round > 0) mbar_wait_backoff(&ring.empty[s], (round - 1) & 1);
-      int row = 0;
-      if (lane == 0) row = static_cast<int>(atomicAdd(&p.ws->next_row, 1u));
-      row = __shfl_sync(0xffffffffu, row, 0);
-      if (row >= p.rows) {
-        if (lane == 0) {
-          ring.meta[s].row = -1;
-          mbar_arrive(&ring.full[s]);
-        }
-        break;
-      }
-      const float w = token_weight_warp(p, row, lane);
-      if (lane == 0) {
-        const float* grow = logits + static_cast<size_t>(row) * p.V;
-        if (w != 0.0f) {
-          mbar_expect_tx(&ring.full[s], row_bytes);
-          tma_load_1d(ring.stage(s), grow, row_bytes, &ring.full[s]);
-        }
-        RingMeta mt;
-        mt.row = row;
-        mt.w = w;
-        mt.i0 = static_cast<int>(p.xt[row]);
-        mt.i1 = static_cast<int>(p.x0[row]);
-        load_betas(p, row / p.L, mt.f0, mt.f1);
-        mt.f2 = (w != 0.0f) ? __ldg(grow + mt.i0) : 0.0f;
-        mt.f3 = (w != 0.0f) ? __ldg(grow + mt.i1) : 0.0f;
-        mt.r0 = mt.r1 = mt.r2 = 0u;
-        ring.meta[s] = mt;
-        mbar_arrive(&ring.full[s]);
-      }
-      if (++s == nstages) { s = 0; ++round; }
-    }
-    return;
-  }
-
-  // ===== consumers =====
-  const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
-  RedRing red{s_red, 0};
-  StageRow<NT> row;
-  int s = 0;
-  uint32_t round = 0;
-  for (;;) {
-    mbar_wait(&ring.full[s], round & 1);
-    const RingMeta mt = ring.meta[s];
-    if (mt.row < 0) break;
-    float* grad_row = BWD ? static_cast<float*>(p.grad) + static_cast<size_t>(mt.row) * p.V : nullptr;
-    if (mt.w == 0.0f) {
-      ring_release(ring, s);
-      if (BWD) {
-        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        for (int vi = tid; vi < p.V / 4; vi += NT) stg_stream_v4(reinterpret_cast<uint4*>(grad_row) + vi, z4);
-      }
-      if (tid == 0) p.ws->kl_tok[mt.row] = 0.0f;
-    } else {
-      row.bind(ring.stage(s), p.V, tid);
-      const float kl = kl_row_math<NT, BWD, float>(row, p.V, mt.i0, mt.i1, mt.f2, mt.f3, mt.f0, mt.f1, mt.w * gscale, red,
-                                                   grad_row);
-      ring_release(ring, s);
-      if (tid == 0) p.ws->kl_tok[mt.row] = kl;
-    }
-    if (++s == nstages) { s = 0; ++round; }
-  }
-  kl_epilogue<NT>(p, s_red, &s_flag, tid);
-}
-
-// ------------------------------------------------------------------------------------------------
 // generic path: any V <= FDDM_MAX_VOCAB, any alignment; the row is an fp32 copy in shared memory
 // ------------------------------------------------------------------------------------------------
 template <typename T, int NT, bool BWD>
@@ -550,33 +439,6 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
                        (!BWD || reinterpret_cast<uintptr_t>(p.grad) % 16 == 0);
   const int sms = num_sms();
   KernelScope ks(BWD ? "kl_rows_fwdbwd" : "kl_rows_fwd", stream);
-  if (std::is_same<T, float>::value && aligned && getenv("FDDM_KL_REG") == nullptr) {
-    // streamed kernel: resident CTAs limited by shared memory (one stage each; more rows in flight beat
-    // a deeper ring)
-    const size_t stage = (row_bytes + 127) & ~size_t(127);
-    int ctas = static_cast<int>((216 * 1024) / (stage + 2560));
-    int st = 1;
-    if (const char* e = getenv("FDDM_KL_CTAS")) ctas = std::min(ctas, atoi(e));            // experiment knobs
-    if (const char* e = getenv("FDDM_KL_STAGES")) st = std::max(1, atoi(e));
-    ctas = std::min(ctas, 6);
-    while (ctas > 1 && static_cast<size_t>(ctas) * (stage * st + 2560) > 216 * 1024) --ctas;
-    if (ctas >= 3) {
-      const size_t smem = stage * st + 128;
-      const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * ctas));
-#define FDDM_KL_STREAMED(NT_, CTAS_)                                                                        \
-  do {                                                                                                      \
-    auto kfn = kl_rows_streamed_kernel<NT_, BWD, CTAS_>;                                                    \
-    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-    kfn<<<grid, NT_ + 32, smem, stream>>>(p, st, static_cast<uint32_t>(stage));                             \
-  } while (0)
-      if (ctas >= 6) FDDM_KL_STREAMED(128, 6);
-      else if (ctas >= 4) FDDM_KL_STREAMED(128, 4);
-      else FDDM_KL_STREAMED(256, 3);
-#undef FDDM_KL_STREAMED
-      FDDM_LAUNCH_OK();
-      return FDDM_OK;
-    }
-  }
   if (aligned && p.V <= 32768) {
     int nt, ept;
     if (p.V <= 4096) { nt = 128; ept = 32; }

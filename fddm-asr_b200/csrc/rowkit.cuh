@@ -124,59 +124,6 @@ struct RegRow {
 };
 
 // ------------------------------------------------------------------------------------------------
-// StageRow: an fp32 row that STAYS in the shared-memory stage the TMA copy filled (V % 4 == 0, 16-byte
-// aligned); every pass streams over it with 128-bit LDS, pass results that must persist (exp) are written
-// back in place.  Thread `tid` owns the vectors tid, tid+NT, ...  No registers hold the row, so the
-// kernels built on it fit 4-6 CTAs per SM: rows in flight are limited by shared memory, not registers.
-// ------------------------------------------------------------------------------------------------
-template <int NT>
-struct StageRow {
-  static constexpr int N = 4;
-  float4* s4;
-  int nvec, tid;
-  __device__ __forceinline__ void bind(void* stage, int V, int tid_) {
-    s4 = reinterpret_cast<float4*>(stage); nvec = V / 4; tid = tid_;
-  }
-  template <class F>
-  __device__ __forceinline__ void for_each_ro(F&& f) {
-#pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      const float4 v = s4[vi];
-      f(vi * 4, v.x); f(vi * 4 + 1, v.y); f(vi * 4 + 2, v.z); f(vi * 4 + 3, v.w);
-    }
-  }
-  template <class F>
-  __device__ __forceinline__ void for_each(F&& f) {          // read-modify-write
-#pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      float4 v = s4[vi];
-      f(vi * 4, v.x); f(vi * 4 + 1, v.y); f(vi * 4 + 2, v.z); f(vi * 4 + 3, v.w);
-      s4[vi] = v;
-    }
-  }
-  template <class F4, class F1>
-  __device__ __forceinline__ void for_each4(F4&& f4, F1&&) {
-#pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      const float4 v = s4[vi];
-      float e[4] = {v.x, v.y, v.z, v.w};
-      f4(e);
-    }
-  }
-  template <class G4, class G1>
-  __device__ __forceinline__ void store4k(float* dst, G4&& g4, G1&&) {
-#pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      const float4 v = s4[vi];
-      const float e[4] = {v.x, v.y, v.z, v.w};
-      float o[4];
-      g4(vi * 4, e, o);
-      stg_stream_v4(reinterpret_cast<uint4*>(dst) + vi, Vec16<float>::pack(o));
-    }
-  }
-};
-
-// ------------------------------------------------------------------------------------------------
 // SmemRow: generic path, the row is an fp32 array in shared memory (any V, any alignment).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int NT>

@@ -20,7 +20,10 @@ constexpr float kNegInf = -3.0e38f;   // finite stand-in for -inf in padded lane
 // RegRow: the row lives in EPT fp32 registers per thread.  Thread `tid` owns the 16-byte vectors
 // tid, tid+NT, tid+2NT, ... of the row; lanes past the end of the row are inactive.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, int EPT>
+// TIGHT: the launcher guarantees nvec > (NVEC-1)*NT, i.e. every thread's first NVEC-1 vectors exist and only
+// the last one needs a bounds check -- the per-vector predicates (ISETP/BRA/BSSY/BSYNC around every unrolled
+// body, ~18 % of the KL kernel's instructions) disappear from all but one vector per pass.
+template <typename T, int NT, int EPT, bool TIGHT = false>
 struct RegRow {
   static constexpr int N = Vec16<T>::N;       // elements per 16-byte vector
   static constexpr int NVEC = EPT / N;
@@ -28,6 +31,10 @@ struct RegRow {
   float v[EPT];
   int nvec;                                   // vectors in the row (V / N)
   int tid;
+  __device__ __forceinline__ bool has(int j, int vi) const {
+    if (TIGHT && j < NVEC - 1) return true;
+    return vi < nvec;
+  }
 
   __device__ __forceinline__ void load_from_smem(const void* stage, int V, int tid_) {
     tid = tid_;
@@ -36,7 +43,7 @@ struct RegRow {
 #pragma unroll
     for (int j = 0; j < NVEC; ++j) {
       const int vi = j * NT + tid;
-      if (vi < nvec) {
+      if (has(j, vi)) {
         Vec16<T>::unpack(s[vi], &v[j * N]);
       } else {
 #pragma unroll
@@ -50,7 +57,7 @@ struct RegRow {
 #pragma unroll
     for (int j = 0; j < NVEC; ++j) {
       const int vi = j * NT + tid;
-      if (vi < nvec) {
+      if (has(j, vi)) {
 #pragma unroll
         for (int e = 0; e < N; ++e) f(vi * N + e, v[j * N + e]);
       }
@@ -73,7 +80,7 @@ struct RegRow {
 #pragma unroll
     for (int j = 0; j < NVEC; ++j) {
       const int vi = j * NT + tid;
-      if (vi < nvec) {
+      if (has(j, vi)) {
 #pragma unroll
         for (int q = 0; q < N / 4; ++q) f4(&v[j * N + 4 * q]);
       }
@@ -85,7 +92,7 @@ struct RegRow {
 #pragma unroll
     for (int j = 0; j < NVEC; ++j) {
       const int vi = j * NT + tid;
-      if (vi < nvec) {
+      if (has(j, vi)) {
         float o[N];
 #pragma unroll
         for (int q = 0; q < N / 4; ++q) g4(&v[j * N + 4 * q], &o[4 * q]);
@@ -99,7 +106,7 @@ struct RegRow {
 #pragma unroll
     for (int j = 0; j < NVEC; ++j) {
       const int vi = j * NT + tid;
-      if (vi < nvec) {
+      if (has(j, vi)) {
         float o[N];
 #pragma unroll
         for (int q = 0; q < N / 4; ++q) g4(vi * N + 4 * q, &v[j * N + 4 * q], &o[4 * q]);
@@ -113,7 +120,7 @@ struct RegRow {
 #pragma unroll
     for (int j = 0; j < NVEC; ++j) {
       const int vi = j * NT + tid;
-      if (vi < nvec) {
+      if (has(j, vi)) {
         float o[N];
 #pragma unroll
         for (int e = 0; e < N; ++e) o[e] = g(vi * N + e, v[j * N + e]);

@@ -281,7 +281,7 @@ __device__ __forceinline__ void kl_epilogue(const KlParams& p, float* red, int* 
 // ------------------------------------------------------------------------------------------------
 // fast path: TMA ring + register-resident rows
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, int EPT, bool BWD, bool TIGHT>
+template <typename T, int NT, int EPT, bool BWD>
 __global__ void __launch_bounds__(NT + 32, (NT <= 256 ? 2 : 1))
 kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -319,15 +319,6 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
         }
         break;
       }
-      // the copy goes out first (whether the row is needed is one mask byte); the token weight (a warp
-      // reduction over the sample's mask row) and the rest of the metadata are prepared under its latency,
-      // and the stage becomes visible to the consumers with the arrive at the end
-      const bool on = (p.mask == nullptr) || (p.mask[row] != 0);
-      if (lane == 0 && on) {
-        mbar_expect_tx(&ring.full[s], row_bytes);
-        tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
-                    row_bytes, &ring.full[s]);
-      }
       const float w = token_weight_warp(p, row, lane);
       if (lane == 0) {
         RingMeta mt;
@@ -339,7 +330,13 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
         mt.f2 = 0.0f; mt.f3 = 0.0f;
         mt.r0 = mt.r1 = mt.r2 = 0u;
         ring.meta[s] = mt;
-        mbar_arrive(&ring.full[s]);
+        if (w != 0.0f) {
+          mbar_arrive_expect_tx(&ring.full[s], row_bytes);
+          tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
+                      row_bytes, &ring.full[s]);
+        } else {
+          mbar_arrive(&ring.full[s]);
+        }
       }
       if (++s == nstages) { s = 0; ++round; }
     }
@@ -349,9 +346,9 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
   // ===== consumers =====
   const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
   RedRing red{s_red, 0};
-  RegRow<T, NT, EPT, TIGHT> row;
+  RegRow<T, NT, EPT> row;
   row.tid = tid;
-  row.nvec = p.V / RegRow<T, NT, EPT, TIGHT>::N;
+  row.nvec = p.V / RegRow<T, NT, EPT>::N;
   int s = 0;
   uint32_t round = 0;
   for (;;) {
@@ -452,12 +449,9 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
     if (plan.nstages >= 1) {
       const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
       const uint32_t sb = static_cast<uint32_t>((row_bytes + 127) & ~size_t(127));
-      // tight: every thread's first NVEC-1 vectors exist (see RegRow)
-      const int nvec = p.V / Vec16<T>::N, nvec_thr = ept / Vec16<T>::N;
-      const bool tight = nvec > (nvec_thr - 1) * nt;
 #define FDDM_KL_LAUNCH(NT_, EPT_)                                                                           \
   do {                                                                                                      \
-    auto kfn = tight ? kl_rows_ring_kernel<T, NT_, EPT_, BWD, true> : kl_rows_ring_kernel<T, NT_, EPT_, BWD, false>; \
+    auto kfn = kl_rows_ring_kernel<T, NT_, EPT_, BWD>;                                                      \
     FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                       static_cast<int>(plan.smem_bytes)));                                  \
     kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb);                                  \

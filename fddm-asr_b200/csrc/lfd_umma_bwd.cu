@@ -18,6 +18,8 @@
 //
 // Warp roles as in lfd_umma.cu: warp 0 TMA producer, warp 1 MMA issuer (one lane) + TMEM owner, warps 2..5
 // epilogue (TMEM lane quarter = warp id % 4).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "umma_common.cuh"
@@ -43,6 +45,36 @@ struct BwdParams {
   float* partial;                        // [T * Bp/32][D] fp32
 };
 
+// ---- thread-block-cluster helpers (CL = 2: the two CTAs of a cluster work on the same n-tile and each loads
+// half of the G tile, multicast into both CTAs' shared memory -> the L2 -> SM operand traffic, which bounds this
+// kernel, drops from 48 to 32 KB per k-block) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy delivered to the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier
+// at the same offset receives the complete_tx for the bytes written there
+__device__ __forceinline__ void tma_load_1d_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// MMA-completion arrive on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void unpack_bf16x8(const uint4& v, float* f) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -52,17 +84,21 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& v, float* f) {
   }
 }
 
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t s_full[kBwdStages], s_empty[kBwdStages], s_acc_full[2], s_acc_empty[2];
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (tid == 0) {
     for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 1);
+      mbar_init(&s_empty[s], CL);                  // one MMA-completion arrive from every CTA of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_acc_full[b], 1);
@@ -77,7 +113,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();                  // peers' barriers are initialised before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
@@ -89,9 +126,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
     const int64_t plane_rows = op == 0 ? p.R_pad : p.D_pad;
     const uint32_t bytes = op == 0 ? kBM * 16u : kBwdBN * 16u;
     const uint32_t dst_off = (op == 0 ? pl * kTileA : 2 * kTileA + pl * kTileB) + static_cast<uint32_t>(c) * bytes;
+    // the G tile's 8 copies are shared out over the cluster: this CTA issues the chunk columns c with c % CL == rank
+    const bool mine = lane < 16 && (op == 0 || (c % CL) == rank);
     uint32_t it = 0;
-    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
-      const int64_t m0 = static_cast<int64_t>(w / p.tiles_n) * kBM, n0 = static_cast<int64_t>(w % p.tiles_n) * kBwdBN;
+    for (int w = cluster_id; w < p.total; w += num_clusters) {
+      const int64_t m0 = (static_cast<int64_t>(w / p.tiles_n) * CL + rank) * kBM;
+      const int64_t n0 = static_cast<int64_t>(w % p.tiles_n) * kBwdBN;
       const int64_t mn0 = op == 0 ? m0 : n0;
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
         const int s = static_cast<int>(it % kBwdStages);
@@ -99,10 +139,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
         if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1);
         if (lane == 0) mbar_arrive_expect_tx(&s_full[s], kBwdStageBytes);
         __syncwarp();
-        if (lane < 16) {
+        if (mine) {
           const int64_t cc = static_cast<int64_t>(kb) * (kBK / 8) + c;
-          tma_load_1d(smem + static_cast<size_t>(s) * kBwdStageBytes + dst_off, plane + (cc * plane_rows + mn0) * 8, bytes,
-                      &s_full[s]);
+          uint8_t* dst = smem + static_cast<size_t>(s) * kBwdStageBytes + dst_off;
+          const __nv_bfloat16* src = plane + (cc * plane_rows + mn0) * 8;
+          if (CL > 1 && op == 1) tma_load_1d_multicast(dst, src, bytes, &s_full[s], kMask);
+          else tma_load_1d(dst, src, bytes, &s_full[s]);
         }
       }
     }
@@ -112,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
       const uint32_t idesc = make_instr_desc(0, 0, kBwdBN);
       constexpr uint32_t csA = kBM * 16u, csB = kBwdBN * 16u;       // bytes between chunk columns (K-major tiles)
       uint32_t it = 0, local = 0;
-      for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++local) {
+      for (int w = cluster_id; w < p.total; w += num_clusters, ++local) {
         const uint32_t buf = local & 1, use = local >> 1;
         if (use > 0) {                                               // the epilogue must have drained this accumulator
           mbar_wait(&s_acc_empty[buf], (use - 1) & 1);
@@ -138,7 +180,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
               accum = 1;
             }
           }
-          umma_commit(&s_empty[s]);                                  // stage reusable once these MMAs have read it
+          // stage reusable once these MMAs have read it -- in EVERY CTA whose producer writes into it
+          if (CL > 1) umma_commit_multicast(&s_empty[s], kMask);
+          else umma_commit(&s_empty[s]);
         }
         umma_commit(&s_acc_full[buf]);                               // accumulator complete
       }
@@ -148,8 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
     // ===== epilogue =====
     const int q = warp & 3;                                          // TMEM lane quarter of this warp
     uint32_t local = 0;
-    for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++local) {
-      const int64_t m0 = static_cast<int64_t>(w / p.tiles_n) * kBM;
+    for (int w = cluster_id; w < p.total; w += num_clusters, ++local) {
+      const int64_t m0 = (static_cast<int64_t>(w / p.tiles_n) * CL + rank) * kBM;
       const int n0 = (w % p.tiles_n) * kBwdBN;
       const uint32_t buf = local & 1, use = local >> 1;
       const int64_t r0 = m0 + q * 32, r = r0 + lane;                 // packed rows of this warp / lane
@@ -228,7 +272,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();                  // no CTA leaves while a peer may still write into it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -254,17 +299,39 @@ int umma_bwd_gemm(const PackedOperand& Z, const PackedOperand& G, const PackedOp
   p.D = static_cast<int>(D);
   p.tiles_n = static_cast<int>((D + kBwdBN - 1) / kBwdBN);
   p.num_kb = static_cast<int>((D + kBK - 1) / kBK);
-  const int64_t tiles_m = (rows.rows_packed + kBM - 1) / kBM;        // R_pad is a multiple of 256 >= rows_packed
-  const int64_t total = tiles_m * p.tiles_n;
-  FDDM_CHECK_ARG(total < (1ll << 31), "umma_bwd_gemm: too many tiles");
+  static const int cl = [] {                                          // FDDM_BWD_CLUSTER=1 falls back to single CTAs
+    const char* e = getenv("FDDM_BWD_CLUSTER");
+    return (e != nullptr && e[0] == '1') ? 1 : 2;
+  }();
+  int64_t tiles_m = (rows.rows_packed + kBM - 1) / kBM;              // R_pad is a multiple of 256 >= rows_packed
+  tiles_m = (tiles_m + cl - 1) / cl * cl;                            // whole clusters (the extra tile is all zeros)
+  const int64_t total = tiles_m / cl * p.tiles_n;                    // work items per cluster
+  FDDM_CHECK_ARG(total < (1ll << 31) && tiles_m * kBM <= Z.R_pad, "umma_bwd_gemm: tile grid");
   p.total = static_cast<int>(total);
   p.Bn = rows.B; p.Bp = rows.Bp; p.Tn = rows.T;
   p.alpha = alpha; p.dz = dz; p.partial = partial;
   const size_t smem = static_cast<size_t>(kBwdStages) * kBwdStageBytes;
-  FDDM_CUDA_OK(cudaFuncSetAttribute(umma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int grid = static_cast<int>(std::min<int64_t>(total, num_sms()));
+  const int clusters = static_cast<int>(std::min<int64_t>(total, num_sms() / cl));
   KernelScope ks("umma_bwd_persistent (z~ G + bn partials)", stream);
-  umma_bwd_kernel<<<grid, kThreads, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * cl));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cl);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cl == 2) {
+    FDDM_CUDA_OK(cudaFuncSetAttribute(umma_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FDDM_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_bwd_kernel<2>, p));
+  } else {
+    FDDM_CUDA_OK(cudaFuncSetAttribute(umma_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FDDM_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_bwd_kernel<1>, p));
+  }
   FDDM_LAUNCH_OK();
   return FDDM_OK;
 }

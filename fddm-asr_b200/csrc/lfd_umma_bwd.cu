@@ -201,17 +201,32 @@ __global__ void __launch_bounds__(kThreads, 1) umma_bwd_kernel(const BwdParams p
       const bool t_ok = t < p.Tn, row_ok = t_ok && b < p.Bn;
       float* orow = p.dz + (static_cast<int64_t>(b) * p.Tn + t) * p.D;
       float* prow = p.partial + (r0 >> 5) * p.D;
+      // z~ of the statistics tensor for (r, n0+c .. +15): two chunk columns, hi + lo, 16-byte loads contiguous
+      // across the 32 lanes.  They do not depend on the accumulator, and a chunk's four loads cost a full
+      // DRAM/L2 round trip (the first version waited for them chunk by chunk: 35 % of all stall samples, the
+      // epilogue -- not the tensor pipe -- set the tile time).  So kPre chunks are kept in flight in registers (this
+      // kernel runs one CTA of 192 threads per SM: registers are plentiful), and the first kPre are issued BEFORE
+      // the wait for the accumulator, i.e. under the main loop that is still producing it.
+      constexpr int kPre = 8, kChunks = kBwdBN / 16;
+      uint4 zq[kPre][4];
+      auto z_load = [&](int slot, int c) {
+        const int64_t cc = (n0 + c) >> 3;                              // always inside the padded planes
+        zq[slot][0] = __ldg(reinterpret_cast<const uint4*>(p.s_hi + (cc * p.R_pad + r) * 8));
+        zq[slot][1] = __ldg(reinterpret_cast<const uint4*>(p.s_lo + (cc * p.R_pad + r) * 8));
+        zq[slot][2] = __ldg(reinterpret_cast<const uint4*>(p.s_hi + ((cc + 1) * p.R_pad + r) * 8));
+        zq[slot][3] = __ldg(reinterpret_cast<const uint4*>(p.s_lo + ((cc + 1) * p.R_pad + r) * 8));
+      };
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) z_load(i, i * 16);
       mbar_wait(&s_acc_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * kBwdBN + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c = 0; c < kBwdBN && n0 + c < p.D; c += 16) {
-        // z~ of the statistics tensor for (r, n0+c .. +15): two chunk columns, hi + lo, 16-byte loads that are
-        // contiguous across the 32 lanes (issued before the TMEM load so their latency overlaps it)
-        const int64_t cc = (n0 + c) >> 3;
-        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(p.s_hi + (cc * p.R_pad + r) * 8));
-        const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(p.s_lo + (cc * p.R_pad + r) * 8));
-        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(p.s_hi + ((cc + 1) * p.R_pad + r) * 8));
-        const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(p.s_lo + ((cc + 1) * p.R_pad + r) * 8));
+#pragma unroll
+      for (int ci = 0; ci < kChunks; ++ci) {
+        const int c = ci * 16;
+        if (n0 + c >= p.D) break;
+        const uint4 h0 = zq[ci % kPre][0], l0 = zq[ci % kPre][1], h1 = zq[ci % kPre][2], l1 = zq[ci % kPre][3];
+        if (ci + kPre < kChunks) z_load(ci % kPre, c + kPre * 16);
         float v[16];
         tmem_ld16(taddr + static_cast<uint32_t>(c), v);
 #pragma unroll

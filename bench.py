@@ -395,8 +395,14 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
+    overlap = world > 1 and args.collectives == "overlap"
+    nccl_ctas = int(os.environ.get("NCCL_MAX_CTAS", "8"))
     if world > 1:
         import torch.distributed as dist
+        if overlap:
+            # the two forward all-reduces of L_fd run on a side stream under the KL / jump kernels: NCCL is held to
+            # a few CTAs and the persistent row kernels leave exactly that many SMs free
+            os.environ.setdefault("NCCL_MAX_CTAS", str(nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     if args.gpus != world and rank == 0:
@@ -428,6 +434,8 @@ def run_gpu(args):
     for k in feats:
         d[k].requires_grad_(kind == "train")
 
+    if overlap:
+        fb.set_sm_reserve(nccl_ctas)
     sch = fb.DiscreteDiffusionScheduler(K=V, T=T_TRAIN, device=dev)
     # multi-GPU: the KL scalar is folded into the one scalar all-reduce at the end of the step
     ad = fb.SchedulerAdapter(sch, group=group, defer_reduce=(D > 0))
@@ -451,9 +459,7 @@ def run_gpu(args):
             dd[k].grad = None
         lfd_op = None
         if D > 0:
-            # (overlapping the all-reduces with the persistent row kernels on a side stream was measured at N=8
-            #  and is slower -- the collective's CTAs wait on peers while holding SMs -- so they stay in order)
-            lfd_op = fb.LfdPipeline(dd["za"], dd["zb"], LAMBDA, group=group, overlap=False)
+            lfd_op = fb.LfdPipeline(dd["za"], dd["zb"], LAMBDA, group=group, overlap=overlap)
             lfd_op.stats()                                        # + all-reduce of the batch statistics
         pstate[1:].add_(8)
         xt = ad.sample_q(dd["x0"], dd["t"], philox_state=pstate)
@@ -678,7 +684,9 @@ def run_gpu(args):
                                    + (" (BASELINE configs[4], batch-sharded)" if args.workload == "c5" else "")
                                    + f"; step = {what}",
                        "global_batch": Bg, "seq_len": L, "vocab": V, "d_proj": D, "T": T_TRAIN,
-                       "parallelism": f"batch-sharded x{world}" + (" (NCCL all-reduce: KL scalar, L_fd stats/cov/bn sums)" if world > 1 else ""),
+                       "parallelism": f"batch-sharded x{world}" + (" (NCCL all-reduce: KL scalar, L_fd stats/cov/bn sums"
+                                                                     + (f"; the two forward all-reduces overlap the KL / jump kernels, {nccl_ctas} SMs reserved" if overlap else "")
+                                                                     + ")" if world > 1 else ""),
                        "sampling_mode": smp.sampling_mode, "greedy": smp.greedy,
                        "l2": f"inputs {h2d / 1e6:.0f} MB/step per GPU > 126 MB L2 (no flush needed)"},
             "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -764,6 +772,8 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--sampling-mode", default="exact", choices=["exact", "fast"], help="c3 only")
     ap.add_argument("--greedy", action="store_true", help="c3 only: argmax instead of Categorical")
+    ap.add_argument("--collectives", default="overlap", choices=["overlap", "serial"],
+                    help="N>1: run L_fd's forward all-reduces under the KL / jump kernels (side stream) or in order")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and eager_b200 legs")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()

@@ -18,6 +18,7 @@ namespace fddm {
 namespace {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs the backward launches on its own thread
+std::atomic<int> g_sm_reserve{0};     // SMs the persistent row kernels leave free (fddm_set_sm_reserve)
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -75,9 +76,23 @@ KernelScope::~KernelScope() {
   nvtxRangePop();
 }
 
+int row_kernel_sms() {
+  const int n = num_sms() - g_sm_reserve.load(std::memory_order_relaxed);
+  return n > 8 ? n : 8;
+}
+
 }  // namespace fddm
 
 extern "C" {
+int fddm_set_sm_reserve(int n) {
+  if (n < 0 || n > 128) {
+    fddm::set_error("set_sm_reserve: n must be in [0, 128]");
+    return FDDM_EINVAL;
+  }
+  fddm::g_sm_reserve.store(n, std::memory_order_relaxed);
+  return FDDM_OK;
+}
+
 int fddm_profile_enable(int on) {
   using namespace fddm;
   std::lock_guard<std::mutex> lk(g_prof_mu);

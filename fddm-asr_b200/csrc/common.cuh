@@ -24,6 +24,7 @@ namespace fddm {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
+int row_kernel_sms();   // num_sms() minus the SMs reserved for a concurrent collective (fddm_set_sm_reserve)
 
 #define FDDM_CHECK_ARG(cond, ...)            \
   do {                                       \

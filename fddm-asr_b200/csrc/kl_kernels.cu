@@ -437,7 +437,7 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
   const size_t row_bytes = static_cast<size_t>(p.V) * sizeof(T);
   const bool aligned = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
                        (!BWD || reinterpret_cast<uintptr_t>(p.grad) % 16 == 0);
-  const int sms = num_sms();
+  const int sms = row_kernel_sms();
   KernelScope ks(BWD ? "kl_rows_fwdbwd" : "kl_rows_fwd", stream);
   if (aligned && p.V <= 32768) {
     int nt, ept;

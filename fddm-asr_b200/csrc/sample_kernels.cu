@@ -807,7 +807,9 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
   }
   RedRing red{s_red, 0};
   const uint4* sv = reinterpret_cast<const uint4*>(dyn_smem);
-  const bool need_p = (p.flags & FDDM_JUMP_WRITE_P) != 0 || p.argmax_p_out != nullptr;
+  const bool debug_w = (p.flags & FDDM_JUMP_DEBUG_W) != 0;      // test hook: holds the stage like need_p
+  const bool need_p = ((p.flags & FDDM_JUMP_WRITE_P) != 0 || p.argmax_p_out != nullptr) && !debug_w;
+  const bool hold = need_p || debug_w;
 
   for (uint32_t it = 0;; ++it) {
     mbar_wait(&s_full, it & 1);
@@ -836,7 +838,7 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
     }
     const float s_t = (sx[0] + sx[1]) + (sx[2] + sx[3]);
     const float z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(dyn_smem) + xt);
-    if (!need_p) {                         // hand the stage back: the next row's copy starts now
+    if (!hold) {                           // hand the stage back: the next row's copy starts now
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty);
     }
@@ -888,6 +890,12 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
     }
     if (mt.w == 0.0f) {                    // sched:133-134 (delta <= 0): identity
       if (tid == 0) p.x_out[mt.row] = xt;
+      if (debug_w) {                       // the target distribution is the one-hot of x_t
+        T* w_row = static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K;
+        for (int k = tid; k < p.K; k += NT) Vec16<T>::store1(w_row + k, k == xt ? 1.0f : 0.0f);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty);
+      }
       continue;
     }
 
@@ -912,6 +920,22 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
       if (w == (owner >> 5)) mw += corr;
       tot += fmaxf(mw, 0.0f);
       cw[w] = tot;
+    }
+    if (debug_w) {                         // test hook: the normalised target distribution, entry by entry
+      T* w_row = static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K;
+      const float inv_tot = 1.0f / tot;
+      for (int vi = tid; vi < nvec; vi += NT) {
+        float f[N];
+        Vec16<T>::unpack(sv[vi], f);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const float pk = ex2_approx(fmaf(f[e], kLog2e, nm)) * inv_S;
+          f[e] = fmaxf((vi * N + e == xt) ? fmaf(wa_x, pk, wb_x) : fmaf(wa, pk, wb), 0.0f) * inv_tot;
+        }
+        stg_stream_v4(reinterpret_cast<uint4*>(w_row) + vi, Vec16<T>::pack(f));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty);
     }
     const float t1 = tot * ((static_cast<float>(mt.r0 >> 8) + 0.5f) * k2m24);
     int wsel = NW - 1;
@@ -1036,9 +1060,9 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
   const size_t row_bytes = static_cast<size_t>(p.K) * sizeof(T);
   const size_t noise_bytes = (NOISE == 1) ? static_cast<size_t>(p.K) * sizeof(float) : 0;
   bool aligned = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
-                 (!(p.flags & FDDM_JUMP_WRITE_P) || reinterpret_cast<uintptr_t>(p.p_out) % 16 == 0);
+                 (!(p.flags & (FDDM_JUMP_WRITE_P | FDDM_JUMP_DEBUG_W)) || reinterpret_cast<uintptr_t>(p.p_out) % 16 == 0);
   if (NOISE == 1) aligned = aligned && (noise_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
-  const int sms = num_sms();
+  const int sms = row_kernel_sms();
   KernelScope ks(NOISE == 0 ? "jump_rows_greedy" : (NOISE == 1 ? "jump_rows_injected_noise" : "jump_rows_philox"), stream);
   if (NOISE == 2 && aligned && p.temperature == 1.0f && p.work != nullptr && getenv("FDDM_JUMP_CFG") == nullptr) {
     // streamed kernel: one stage per CTA, resident CTAs limited by shared memory
@@ -1186,7 +1210,9 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
   FDDM_CHECK_ARG(B * L < (1ll << 31), "jump_step: too many rows");
   FDDM_CHECK_ARG(!(flags & FDDM_JUMP_EXACT) || coeffs, "jump_step: exact mode needs coeffs");
   FDDM_CHECK_ARG((flags & FDDM_JUMP_EXACT) || alpha_bar || abar_index < 0, "jump_step: fast mode needs alpha_bar");
-  FDDM_CHECK_ARG(!(flags & FDDM_JUMP_WRITE_P) || p_x0_out, "jump_step: WRITE_P needs p_x0_out");
+  FDDM_CHECK_ARG(!(flags & (FDDM_JUMP_WRITE_P | FDDM_JUMP_DEBUG_W)) || p_x0_out, "jump_step: WRITE_P needs p_x0_out");
+  FDDM_CHECK_ARG(!(flags & FDDM_JUMP_DEBUG_W) || ((flags & FDDM_JUMP_SAMPLE) && !exp_noise && temperature == 1.0f),
+                 "jump_step: DEBUG_W is a hook of the in-kernel-RNG flavour (SAMPLE, no injected noise, temperature 1)");
   FDDM_CHECK_ARG(temperature > 0.0f, "jump_step: temperature must be positive");
   if (K > FDDM_MAX_VOCAB) {
     set_error("jump_step: K=%lld exceeds FDDM_MAX_VOCAB=%d", (long long)K, FDDM_MAX_VOCAB);

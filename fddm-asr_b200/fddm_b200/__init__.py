@@ -8,10 +8,11 @@ Host-side mirror of the reference's interfaces over libfddm_b200.so (include/fdd
 There is no CPU path: importing needs the built shared library, ops need CUDA tensors.
 """
 from . import _lib
+from ._lib import set_sm_reserve
 from .scheduler import DiscreteDiffusionScheduler
 from .adapter import SchedulerAdapter
 from .sampler import DiffusionJumpySampler, ModelAdapter
 from .losses import LfdPipeline, lfd_loss
 
 __all__ = ["DiscreteDiffusionScheduler", "SchedulerAdapter", "DiffusionJumpySampler", "ModelAdapter", "lfd_loss", "LfdPipeline",
-           "_lib"]
+           "_lib", "set_sm_reserve"]

@@ -41,6 +41,7 @@ SIGNATURES = {
     "fddm_version": (_i32, []),
     "fddm_last_error": (C.c_char_p, []),
     "fddm_launch_count": (_i64, []),
+    "fddm_set_sm_reserve": (_i32, [_i32]),
     "fddm_profile_enable": (_i32, [_i32]),
     "fddm_profile_read": (_i64, [_vp, _i64]),
     "fddm_q_sample_dense": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp]),
@@ -120,6 +121,11 @@ def stream_ptr(device: torch.device) -> int:
 
 def launch_count() -> int:
     return int(lib.fddm_launch_count())
+
+
+def set_sm_reserve(n: int) -> None:
+    """SMs the persistent row kernels leave free for a collective running concurrently on another stream."""
+    check(lib.fddm_set_sm_reserve(int(n)), "set_sm_reserve")
 
 
 def profile_enable(on: bool) -> None:

@@ -12,8 +12,10 @@ covariance and the batch-norm backward sums are the only three collectives.
 
 `LfdPipeline` exposes the same computation in stages so that a batch-sharded training step can interleave
 (or, with overlap=True, overlap on a high-priority side stream) the two forward all-reduces with the
-independent KL / resampling kernels.  Measured on 8 B200s the overlap LOSES (the collective's CTAs spin on
-their peers while holding SMs the persistent row kernels need), so it is off by default:
+independent KL / resampling kernels.  The persistent row kernels fill every SM, so a concurrent collective
+must be given SMs of its own (`fddm_b200.set_sm_reserve(n)` with n = the collective's CTA count, e.g.
+NCCL_MAX_CTAS); without that reservation the overlap LOSES (round 1, 8 B200s: the collective's CTAs queue
+behind / spin next to the persistent CTAs):
 
     op = LfdPipeline(z_a, z_b, lam, eps, group=pg)
     op.stats()            # statistics kernel + async all-reduce
@@ -56,7 +58,8 @@ class _AsyncAllReduce:
         comm = _comm_stream(dev)
         ready = torch.cuda.Event()
         ready.record(cur)
-        x.record_stream(comm)
+        if not torch.cuda.is_current_stream_capturing():        # (a captured graph keeps its pool alive itself)
+            x.record_stream(comm)
         with torch.cuda.stream(comm):
             comm.wait_event(ready)
             torch.distributed.all_reduce(x, op=torch.distributed.ReduceOp.SUM, group=group)

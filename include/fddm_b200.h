@@ -46,6 +46,10 @@ typedef enum {
 #define FDDM_JUMP_EXACT   0x1      /* sampling_mode == "exact" (else "fast"), sampler:192-209 */
 #define FDDM_JUMP_SAMPLE  0x2      /* Categorical sampling (else argmax), sampler:153-162 / 212-215 */
 #define FDDM_JUMP_WRITE_P 0x4      /* also write softmax(logits) = p_x0 in the logits dtype, sampler:189 */
+#define FDDM_JUMP_DEBUG_W 0x8      /* test hook of the in-kernel-RNG flavour (SAMPLE, no injected noise, temperature 1):
+                                      p_x0_out receives, instead of p_x0, the NORMALISED target distribution the draw
+                                      is taken from (the Delta-step posterior / alpha-bar mix), so that the fast
+                                      arithmetic of that flavour can be compared with the oracle entry by entry */
 
 int fddm_version(void);
 const char* fddm_last_error(void);
@@ -58,6 +62,12 @@ int64_t fddm_launch_count(void);
  * fddm_profile_read synchronises the recorded events and writes "kernel<TAB>launches<TAB>total_ms" lines
  * into buf (NUL-terminated) when cap suffices; returns the bytes needed. */
 int fddm_profile_enable(int on);
+
+/* The persistent row kernels (KL, jump step) normally fill every SM.  A caller that runs a collective
+ * (NCCL all-reduce) concurrently on another stream reserves the SMs that collective's CTAs need, so that it
+ * is never queued behind the persistent CTAs: the row kernels then launch (SMs - n) * resident CTAs and their
+ * dynamic row scheduler does the rest.  Process-wide; 0 restores the default. */
+int fddm_set_sm_reserve(int n);
 int64_t fddm_profile_read(char* buf, int64_t cap);
 
 /* ------------------------------------------------------------------------------------------------

@@ -36,7 +36,8 @@ struct KlParams {
   const int64_t* xt;
   const int64_t* x0;
   const int64_t* t;
-  const uint8_t* mask;
+  const uint8_t* mask;       // [B, L] bytes (non-zero = valid), or
+  const float* maskf;        // [B, L] fp32 weights -- the reference multiplies by x_mask.float() (train.py:250)
   const float* betas;
   const float* grad_scale;
   KlWorkspace* ws;
@@ -59,6 +60,14 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 // (train.py:249-255).  Evaluated by one full warp.
 __device__ __forceinline__ float token_weight_warp(const KlParams& p, int row, int lane) {
   const int b = row / p.L;
+  if (p.maskf != nullptr) {
+    const float* mrow = p.maskf + static_cast<size_t>(b) * p.L;
+    float c = 0.0f;
+    for (int l = lane; l < p.L; l += 32) c += mrow[l];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return p.maskf[row] * (1.0f / (c + kEps)) * p.inv_bdiv;
+  }
   if (p.mask == nullptr) return (1.0f / static_cast<float>(p.L)) * p.inv_bdiv;
   const uint8_t* mrow = p.mask + static_cast<size_t>(b) * p.L;
   int c = 0;
@@ -235,10 +244,15 @@ __device__ __forceinline__ void kl_finalize(const KlParams& p, float* red, int t
   for (int b = warp; b < p.B; b += NW) {
     float s = 0.0f;
     int c = 0;
+    float cf = 0.0f;
     for (int l = lane; l < p.L; l += 32) {
       const size_t i = static_cast<size_t>(b) * p.L + l;
       const float k = __ldcg(&p.ws->kl_tok[i]);
-      if (p.mask) {
+      if (p.maskf) {
+        const float wgt = p.maskf[i];
+        cf += wgt;
+        s += (wgt != 0.0f) ? k * wgt : 0.0f;
+      } else if (p.mask) {
         const bool on = p.mask[i] != 0;
         c += on;
         s += on ? k : 0.0f;
@@ -249,7 +263,9 @@ __device__ __forceinline__ void kl_finalize(const KlParams& p, float* red, int t
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     c = warp_sum_int(c);
-    acc += p.mask ? s / (static_cast<float>(c) + kEps) : s / static_cast<float>(p.L);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cf += __shfl_xor_sync(0xffffffffu, cf, o);
+    acc += p.maskf ? s / (cf + kEps) : (p.mask ? s / (static_cast<float>(c) + kEps) : s / static_cast<float>(p.L));
   }
   if (lane == 0) red[warp] = acc;
   consumer_sync<NT>();
@@ -476,7 +492,7 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
 }
 
 int kl_entry(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
-             const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V, double batch_div,
+             const void* x_mask, int mask_is_f32, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V, double batch_div,
              const float* grad_scale, void* workspace, float* loss_out, void* grad_logits, bool bwd,
              cudaStream_t stream) {
   FDDM_CHECK_ARG(logits && xt && x0 && t && betas && workspace && loss_out, "kl: null pointer argument");
@@ -491,7 +507,9 @@ int kl_entry(const void* logits, int dtype, const int64_t* xt, const int64_t* x0
     return FDDM_EUNSUPPORTED;
   }
   KlParams p;
-  p.logits = logits; p.xt = xt; p.x0 = x0; p.t = t; p.mask = x_mask; p.betas = betas;
+  p.logits = logits; p.xt = xt; p.x0 = x0; p.t = t; p.betas = betas;
+  p.mask = mask_is_f32 ? nullptr : static_cast<const uint8_t*>(x_mask);
+  p.maskf = mask_is_f32 ? static_cast<const float*>(x_mask) : nullptr;
   p.grad_scale = grad_scale; p.ws = static_cast<KlWorkspace*>(workspace); p.loss_out = loss_out;
   p.grad = grad_logits;
   p.T = static_cast<int>(T); p.B = static_cast<int>(B); p.L = static_cast<int>(L); p.V = static_cast<int>(V);
@@ -514,20 +532,21 @@ size_t fddm_kl_workspace_bytes(int64_t B, int64_t L) {
 }
 
 int fddm_kl_forward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
-                    const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
+                    const void* x_mask, int mask_is_f32, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
                     double batch_div, void* workspace, float* loss_out, fddm_stream_t stream) {
   FDDM_API_RANGE();
-  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, betas, T, B, L, V, batch_div, nullptr, workspace, loss_out,
-                        nullptr, false, reinterpret_cast<cudaStream_t>(stream));
+  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, mask_is_f32, betas, T, B, L, V, batch_div, nullptr, workspace,
+                        loss_out, nullptr, false, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fddm_kl_forward_backward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
-                             const uint8_t* x_mask, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
+                             const void* x_mask, int mask_is_f32, const float* betas, int64_t T, int64_t B, int64_t L,
+                             int64_t V,
                              double batch_div, const float* grad_scale, void* workspace, float* loss_out,
                              void* grad_logits, fddm_stream_t stream) {
   FDDM_API_RANGE();
-  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, betas, T, B, L, V, batch_div, grad_scale, workspace,
-                        loss_out, grad_logits, true, reinterpret_cast<cudaStream_t>(stream));
+  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, mask_is_f32, betas, T, B, L, V, batch_div, grad_scale,
+                        workspace, loss_out, grad_logits, true, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fddm_scale_inplace(void* x, int dtype, int64_t n, const float* num, const float* den, fddm_stream_t stream_) {

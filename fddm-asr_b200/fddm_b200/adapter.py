@@ -15,14 +15,16 @@ from . import _lib as L
 from .scheduler import DiscreteDiffusionScheduler
 
 
-def _as_mask_u8(x_mask: Optional[torch.Tensor], B: int, Lq: int) -> Optional[torch.Tensor]:
+def _as_mask(x_mask: Optional[torch.Tensor], B: int, Lq: int) -> Optional[torch.Tensor]:
+    """bool -> uint8 view (non-zero = valid); any other dtype -> fp32 WEIGHTS, because the reference multiplies
+    the per-token KL by `x_mask.float()` (train.py:250): a non-boolean mask weights the tokens."""
     if x_mask is None:
         return None
     if x_mask.shape != (B, Lq):
         raise ValueError(f"x_mask must have shape ({B}, {Lq}), got {tuple(x_mask.shape)}")
     if x_mask.dtype == torch.bool:
         return x_mask.contiguous().view(torch.uint8)
-    return (x_mask != 0).contiguous().view(torch.uint8)       # the reference does x_mask.float()
+    return x_mask.to(torch.float32).contiguous()
 
 
 class _KLTermFn(torch.autograd.Function):
@@ -32,24 +34,25 @@ class _KLTermFn(torch.autograd.Function):
     rescales it in place only if the actual upstream gradient differs."""
 
     @staticmethod
-    def forward(ctx, logits, xt, x0, t, mask_u8, betas, T, batch_div, grad_scale, group):
+    def forward(ctx, logits, xt, x0, t, mask, betas, T, batch_div, grad_scale, group):
         B, Lq, V = logits.shape
         dev = logits.device
         ws = L.zeroed_workspace(dev, "kl", int(L.lib.fddm_kl_workspace_bytes(B, Lq)))
         loss = torch.empty((), dtype=torch.float32, device=dev)
         need_grad = ctx.needs_input_grad[0]
         dt = L.dtype_code(logits)
+        mask_f32 = 1 if (mask is not None and mask.dtype == torch.float32) else 0
         if need_grad:
             grad = torch.empty_like(logits)
             L.check(L.lib.fddm_kl_forward_backward(logits.data_ptr(), dt, xt.data_ptr(), x0.data_ptr(), t.data_ptr(),
-                                                   L.ptr(mask_u8), betas.data_ptr(), T, B, Lq, V, float(batch_div),
+                                                   L.ptr(mask), mask_f32, betas.data_ptr(), T, B, Lq, V, float(batch_div),
                                                    L.ptr(grad_scale), ws.data_ptr(), loss.data_ptr(),
                                                    grad.data_ptr(), L.stream_ptr(dev)), "kl_forward_backward")
             ctx.save_for_backward(grad, grad_scale if grad_scale is not None else torch.empty(0, device=dev))
             ctx.has_scale = grad_scale is not None
         else:
             L.check(L.lib.fddm_kl_forward(logits.data_ptr(), dt, xt.data_ptr(), x0.data_ptr(), t.data_ptr(),
-                                          L.ptr(mask_u8), betas.data_ptr(), T, B, Lq, V, float(batch_div),
+                                          L.ptr(mask), mask_f32, betas.data_ptr(), T, B, Lq, V, float(batch_div),
                                           ws.data_ptr(), loss.data_ptr(), L.stream_ptr(dev)), "kl_forward")
         if group is not None:
             torch.distributed.all_reduce(loss, op=torch.distributed.ReduceOp.SUM, group=group)
@@ -71,7 +74,7 @@ class _KLTermFn(torch.autograd.Function):
 
 class SchedulerAdapter:
     def __init__(self, scheduler: DiscreteDiffusionScheduler, *, grad_scale=None, group=None,
-                 defer_reduce: bool = False):
+                 defer_reduce: bool = False, validate_t: bool = True):
         """`grad_scale`: optional fp32 device scalar (or a zero-argument callable returning one),
         the upstream gradient the training loop will feed into `kl_term` (e.g. the AMP GradScaler's
         scale); folding it into the fused pass avoids a second pass over the gradient.
@@ -84,6 +87,7 @@ class SchedulerAdapter:
         self._grad_scale = grad_scale
         self._group = group
         self._defer = bool(defer_reduce)
+        self._validate_t = bool(validate_t)     # device-side assert 1 <= t <= T (no host sync); the kernels clamp
 
     # -- train.py:180-188 ------------------------------------------------------------------------
     def sample_q(self, x0: torch.Tensor, t: torch.Tensor, *, exp_noise=None, generator=None,
@@ -109,7 +113,11 @@ class SchedulerAdapter:
         betas = self.sch.betas.to(dev)
         if betas.dtype != torch.float32 or not betas.is_contiguous():
             betas = betas.float().contiguous()
-        mask = _as_mask_u8(None if x_mask is None else x_mask.to(dev), B, Lq)
+        mask = _as_mask(None if x_mask is None else x_mask.to(dev), B, Lq)
+        if self._validate_t and not torch.cuda.is_current_stream_capturing():
+            # the reference indexes betas[t-1]: out-of-range t is an IndexError on CPU and a device-side assert
+            # on CUDA.  Same here, without a host sync: an asynchronous device-side assert.
+            torch._assert_async(((t >= 1) & (t <= int(betas.numel()))).all())
         world = 1 if self._group is None else torch.distributed.get_world_size(self._group)
         gs = self._grad_scale() if callable(self._grad_scale) else self._grad_scale
         if gs is not None:

@@ -133,6 +133,12 @@ class DiffusionJumpySampler:
             elif self.philox_state is None:
                 seed, offset = philox_seed_offset(dev, self.generator, 4)
         p_x0 = None
+        if getattr(self, "_debug_weights", False) and sample and noise is None and self.temperature == 1.0:
+            # test hook (FDDM_JUMP_DEBUG_W): p_x0's slot receives the normalised distribution the in-kernel-RNG
+            # flavour draws from, so its fast arithmetic can be checked against the oracle entry by entry
+            flags |= L.JUMP_DEBUG_W
+            want_p = False
+            p_x0 = torch.empty_like(logits)
         if want_p:
             flags |= L.JUMP_WRITE_P
             p_x0 = torch.empty_like(logits)                     # softmax output keeps the logits dtype

@@ -121,7 +121,9 @@ int fddm_q_posterior_multi_dense(const float* xt_prob, const float* x0hat_prob, 
  * variant additionally writes d loss / d logits in the same pass (logits are read exactly once).
  *
  *   logits      [B,L,V] dtype `dtype`           xt, x0  int64 [B,L]        t  int64 [B]
- *   x_mask      uint8/bool [B,L] or NULL (plain mean over L)
+ *   x_mask      NULL (plain mean over L), or [B,L] uint8/bool (mask_is_f32 = 0: non-zero = valid), or [B,L]
+ *               fp32 WEIGHTS (mask_is_f32 = 1): the reference multiplies by x_mask.float() (train:250), so a
+ *               non-boolean mask acts as per-token weights sum_l w KL / (sum_l w + eps)
  *   batch_div   the divisor of the final batch mean (B for one process; the GLOBAL batch when the
  *               batch is sharded over ranks -- then *loss_out is this rank's partial sum / batch_div
  *               and an all-reduce SUM completes it)
@@ -131,11 +133,11 @@ int fddm_q_posterior_multi_dense(const float* xt_prob, const float* x0hat_prob, 
  *   grad_logits [B,L,V] dtype `dtype` (the reference's grad has the logits dtype) */
 size_t fddm_kl_workspace_bytes(int64_t B, int64_t L);
 int fddm_kl_forward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0,
-                    const int64_t* t, const uint8_t* x_mask, const float* betas, int64_t T,
+                    const int64_t* t, const void* x_mask, int mask_is_f32, const float* betas, int64_t T,
                     int64_t B, int64_t L, int64_t V, double batch_div, void* workspace,
                     float* loss_out, fddm_stream_t stream);
 int fddm_kl_forward_backward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0,
-                             const int64_t* t, const uint8_t* x_mask, const float* betas, int64_t T,
+                             const int64_t* t, const void* x_mask, int mask_is_f32, const float* betas, int64_t T,
                              int64_t B, int64_t L, int64_t V, double batch_div,
                              const float* grad_scale, void* workspace, float* loss_out,
                              void* grad_logits, fddm_stream_t stream);

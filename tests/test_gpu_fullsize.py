@@ -1,12 +1,15 @@
 """GPU tests at BASELINE.json's full sizes (configs c2, c3, c4 and the c5 per-GPU shard), where the numpy
-oracle would take minutes: size-independent properties of the domain + consistency between the fused
-kernels and this library's own dense-API kernels (which ARE oracle-checked at small sizes), plus an
-oracle check on a random sample of rows."""
+oracle would take minutes.  The independent checker here is the torch restatement of the reference
+(oracle/fddm_torch_port.py, pinned to the reference-generated golden vectors by the CPU tests) evaluated in
+FP64 ON THE GPU over WHOLE tensors (test_kl_fullsize_vs_port_fp64, test_jumpy_sampler_c3_vs_port,
+test_lfd_fullsize_properties), plus size-independent properties of the domain and consistency between the
+fused kernels and this library's own dense-API kernels."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import fddm_oracle as O
+from oracle import fddm_torch_port as P
 
 pytestmark = pytest.mark.gpu
 T_TRAIN = 200
@@ -79,6 +82,95 @@ def test_kl_fullsize_properties(fb, B, L, V, dtype):
     want = grad * w[..., None]
     gtol = 2e-4 if dtype == torch.float32 else 2e-2               # fp32: includes the reference's own t<=2 noise
     assert np.abs(got - want).max() <= gtol * np.abs(want).max()
+
+
+def port_kl_fp64(xt, x0, logits, t, betas, mask, chunk=8):
+    """KL loss and d loss / d logits of the reference formula (train.py:190-255 as restated in
+    oracle/fddm_torch_port.py) in fp64 on the GPU, over the whole batch, evaluated in batch chunks (the loss is
+    a mean of per-sample terms).  Half-precision logits: softmax in the logits dtype first (quirk Q11)."""
+    B = logits.shape[0]
+    b64 = betas.double()
+    total = 0.0
+    grads = []
+    for i in range(0, B, chunk):
+        sl = slice(i, min(B, i + chunk))
+        lg = logits[sl].double().requires_grad_(True)
+        part = P.kl_term(xt[sl], x0[sl], lg, t[sl], b64, mask[sl]) * ((sl.stop - sl.start) / B)
+        part.backward()
+        total += float(part.detach())
+        grads.append(lg.grad)
+    return total, torch.cat(grads, 0)
+
+
+@pytest.mark.parametrize("tag,B,L,V,dtype", [("c2", 32, 128, 8000, torch.float32),
+                                             ("c5shard", 64, 256, 8000, torch.float32),
+                                             ("c4", 64, 256, 32000, torch.float32),
+                                             ("c4", 64, 256, 32000, torch.bfloat16),
+                                             ("c2", 32, 128, 8000, torch.bfloat16)])
+def test_kl_fullsize_vs_port_fp64(fb, tag, B, L, V, dtype):
+    """Whole-tensor check of the fused KL kernel (loss AND every gradient entry) against the fp64 port at
+    the full BASELINE sizes: 1e-5 relative in fp32, 1e-2 with bf16 logits (north_star bars)."""
+    s = sched(fb, V)
+    ad = fb.SchedulerAdapter(s)
+    logits, x0, mask, t = synth(B, L, V, dtype)
+    xt = ad.sample_q(x0, t)
+    lg = logits.clone().requires_grad_(True)
+    loss = ad.kl_term(xt, x0, lg, t, mask)
+    loss.backward()
+    want, wgrad = port_kl_fp64(xt, x0, logits, t, s.betas, mask)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert abs(float(loss.detach()) - want) <= tol * abs(want), (float(loss.detach()), want)
+    err = float((lg.grad.double() - wgrad).abs().max()) / float(wgrad.abs().max())
+    assert err <= tol, err
+    # per-row check as well (a max-norm over the tensor is dominated by the large-gradient rows): every row
+    # within tol of ITS OWN largest entry, except rows of the t <= 2 samples where the unmodified reference in
+    # fp32 is itself 1.8e-4 away from fp64 (DESIGN.md section 2) -- those get that documented bar
+    rerr = (lg.grad.double() - wgrad).abs().amax(-1) / wgrad.abs().amax(-1).clamp_min(1e-300)
+    small_t = (t <= 2)[:, None].expand(B, L)
+    ok_rows = mask & ~small_t
+    assert float(rerr[ok_rows].max()) <= (2e-5 if dtype == torch.float32 else 2e-2), float(rerr[ok_rows].max())
+    if bool((mask & small_t).any()):
+        assert float(rerr[mask & small_t].max()) <= (6e-4 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_jumpy_sampler_c3_vs_port(fb, mode):
+    """c3 (B=256 L=128 V=8000, T_infer=20 r=5), greedy: the ids every jump hands to the decoder equal the ids
+    the torch port of the reference (fp32, same GPU) produces from the same inputs; a mismatch must be a
+    near-tie of the port's posterior (top-2 within 1e-6 relative)."""
+    B, L, V = 256, 128, 8000
+    s = sched(fb, V)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    steps = [(torch.randn(B, L, V, generator=g, device="cuda") * 3.0) for _ in range(4)]
+    calls = []
+
+    def decoder(x, t, c):
+        calls.append((x.clone(), int(t[0])))
+        return steps[len(calls) - 1]
+
+    smp = fb.DiffusionJumpySampler(s, decoder, K=V, T_train=T_TRAIN, T_infer=20, r=5, greedy=True,
+                                   sampling_mode=mode, device=torch.device("cuda"))
+    x0, p_last = smp.sample(torch.zeros(B, 1, 1, device="cuda"), L)
+    assert [c[1] for c in calls] == [20, 15, 10, 5]
+    nbad = 0
+    for i in range(4):
+        x_t, t_s = calls[i]
+        want, p_x0 = P.jump_once(x_t, steps[i], t_s, 5, s.betas, s.alpha_bar, V, T_TRAIN, 20, sampling_mode=mode, greedy=True)
+        got = calls[i + 1][0] if i < 3 else smp.last_resampled_idx
+        bad = want != got
+        if bool(bad.any()):
+            # re-evaluate the posterior rows in question to certify the near-tie
+            if mode == "exact":
+                oh = torch.zeros(B, L, V, device="cuda").scatter_(-1, x_t.unsqueeze(-1), 1.0)
+                post = P.q_posterior_multi_step(oh, p_x0, torch.full((B,), t_s, device="cuda"), 5, s.betas, T_TRAIN)
+            else:
+                post = smp._alpha_bar_at_t_train(max(0, t_s - 5)) * p_x0 + (1 - smp._alpha_bar_at_t_train(max(0, t_s - 5))) / V
+            top2 = post[bad].topk(2, -1).values
+            assert float(((top2[:, 0] - top2[:, 1]) / top2[:, 0]).max()) < 1e-6
+        nbad += int(bad.sum())
+    assert nbad <= 2
+    np.testing.assert_allclose(p_last.cpu().numpy(), torch.softmax(steps[3], -1).cpu().numpy(), rtol=1e-5, atol=1e-30)
+    assert torch.equal(x0, p_last.argmax(-1))                               # sampler:292 (Q9)
 
 
 @pytest.mark.parametrize("mode", ["exact", "fast"])

@@ -380,17 +380,48 @@ def test_jumpy_sampler_golden_chain(fb, golden, tag, monkeypatch):
     x0, p_last = smp.sample(torch.zeros(B, 1, 1, device="cuda"), L)
     seen = np.stack(dec.seen_x)
     want_seen = golden[f"js_{tag}_x_seen"]
-    # ids fed to the decoder at every jump == the reference's, bit for bit (half dtypes: near-ties allowed)
+    # ids fed to the decoder at every jump == the reference's, bit for bit
     if tdt == torch.float32:
         assert np.array_equal(seen, want_seen)
         assert np.array_equal(x0.cpu().numpy(), golden[f"js_{tag}_x0"])
     else:
-        assert (seen != want_seen).mean() <= 0.05
+        # half dtypes: the posterior is rounded to 8 (bf16) / 11 (fp16) bits, so exact ties between candidates
+        # are common and a 1-ulp difference in the softmax sum flips them.  Every jump is therefore certified
+        # on its own: given the ids OUR chain fed the decoder at jump i, the oracle (same logits, same injected
+        # noise, same half-precision roundings) must produce the ids our chain fed at jump i+1, and any
+        # position where it does not must be a near-tie (<= 2 ulps of the half dtype) in the oracle's scores.
+        io = "bf16" if tdt == torch.bfloat16 else "f16"
+        half_ulps = 2.0 * (2.0 ** 16 if io == "bf16" else 2.0 ** 13)        # 2 half-ulps in fp32 ulps
+        betas, abar = s.betas.cpu().numpy(), s.alpha_bar.cpu().numpy()
+        t_i, nbad = T_infer, 0
+        for i in range(seen.shape[0] - 1):
+            delta = min(r, t_i)
+            E = noise[i].reshape(B, L, K) if noise.size else None
+            want_next, _, p_post = O.jump_once(seen[i], golden[f"js_{tag}_logits"][i], t_i, delta, K=K, T_train=T_train,
+                                               T_infer=T_infer, betas=betas, alpha_bar=abar, sampling_mode=mode,
+                                               posterior_mode=pmode, greedy=bool(greedy), temperature=float(temp),
+                                               exp_noise=E, io_dtype=io)
+
+            def scores(idx, p_post=p_post, E=E):
+                p = p_post[idx]
+                if bool(greedy) or pmode == "max":
+                    return p
+                if float(temp) != 1.0:
+                    p = O.softmax_lastdim(np.log(np.maximum(p, np.float32(1e-12))) / np.float32(temp))
+                return (p / p.sum(dtype=np.float32)) / E[idx]
+            bad = np.argwhere(seen[i + 1] != want_next)
+            for idx in bad:
+                idx = tuple(idx)
+                assert O.near_tie(scores(idx), int(seen[i + 1][idx]), int(want_next[idx]), ulps=half_ulps), \
+                    f"jump {i}: id mismatch at {idx} is not a near-tie of the {io} scores"
+            nbad += len(bad)
+            t_i -= delta
+        assert nbad <= 0.02 * seen[1:].size                                   # ties are common, not the rule
     assert np.array_equal(np.stack(dec.seen_t), golden[f"js_{tag}_t_seen"])
     assert p_last.dtype == tdt and str(golden[f"js_{tag}_p_last_dtype"]) == dt
     tol = FP32_TOL if tdt == torch.float32 else HALF_TOL
-    if np.array_equal(seen, want_seen):
-        np.testing.assert_allclose(p_last.float().cpu().numpy(), golden[f"js_{tag}_p_last"], rtol=tol, atol=1e-30)
+    # p_x0 of the last jump depends only on that jump's logits (not on the chain's history): always checked
+    np.testing.assert_allclose(p_last.float().cpu().numpy(), golden[f"js_{tag}_p_last"], rtol=tol, atol=1e-30)
     info = smp.get_sampling_info()
     assert info["sampling_mode"] == mode and info["K"] == K and info["r"] == r
 
@@ -427,6 +458,64 @@ def test_jump_step_vs_oracle(fb, mode, greedy, temp, B, L, K):
             return (p / p.sum(dtype=np.float32)) / E[idx]
         nbad = certify_ids(ids.cpu().numpy(), want_ids, scores)
         assert nbad <= 1
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("io,B,L,K", [("f32", 4, 8, 8000), ("f32", 3, 5, 4000), ("f32", 2, 4, 32000), ("bf16", 4, 8, 8000)])
+def test_jump_fast_flavour_target_distribution_vs_oracle(fb, mode, io, B, L, K):
+    """The BENCHMARKED jump flavour (in-kernel RNG: MUFU exp/reciprocal, FMA, warp masses from the softmax
+    partials, hierarchical inverse-CDF draw) cannot be compared id by id with the reference; its target
+    distribution can: the FDDM_JUMP_DEBUG_W hook makes the kernel emit the normalised distribution it draws
+    from, which must equal the oracle's Delta-step posterior / alpha-bar mix within 1e-5 (1e-2 for bf16)."""
+    T_train, T_infer, r = 200, 20, 5
+    rng = np.random.default_rng(K + B)
+    s = make_sched(fb, K, T_train)
+    betas, abar = s.betas.cpu().numpy(), s.alpha_bar.cpu().numpy()
+    for t_scalar in (20, 10, 5):
+        delta = min(r, t_scalar)
+        logits = O.round_to_dtype((rng.normal(size=(B, L, K)) * 3).astype(np.float32), io)
+        x_t = rng.integers(0, K, size=(B, L))
+        dec = ReplayDecoder([logits], DT[io])
+        smp = fb.DiffusionJumpySampler(s, dec, K=K, T_train=T_train, T_infer=T_infer, r=r, greedy=False,
+                                       sampling_mode=mode, device=torch.device("cuda"))
+        smp._debug_weights = True
+        ids, w = smp._jump_once(dev(x_t), t_scalar, delta, torch.zeros(B, 1, 1, device="cuda"), L)
+        _, _, p_post = O.jump_once(x_t, logits, t_scalar, delta, K=K, T_train=T_train, T_infer=T_infer, betas=betas,
+                                   alpha_bar=abar, sampling_mode=mode, greedy=True, io_dtype="f32")
+        want = p_post.astype(np.float64)
+        want /= want.sum(-1, keepdims=True)
+        got = w.float().cpu().numpy().astype(np.float64)
+        tol = FP32_TOL if io == "f32" else HALF_TOL
+        assert np.abs(got.sum(-1) - 1).max() < (1e-5 if io == "f32" else 2e-2)
+        assert np.abs(got - want).max() <= tol * want.max(), (np.abs(got - want).max(), want.max())
+        # and the drawn ids are consistent with it: in range, never on a zero-probability entry
+        idn = ids.cpu().numpy()
+        assert idn.min() >= 0 and idn.max() < K
+        assert (np.take_along_axis(want, idn[..., None], -1) > 0).all()
+
+
+def test_jump_philox_offsets_advance_per_jump(fb):
+    """Two consecutive sampling jumps driven by one device-side {seed, offset} draw DIFFERENT variates (the
+    offset is advanced on the device after every jump), and a sample_q call sharing that state is independent
+    of the jump (separate counter domains)."""
+    K, B, L = 4000, 8, 64
+    s = make_sched(fb, K, 200)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    logits = torch.randn(B, L, K, generator=g, device="cuda")
+    x_t = torch.randint(0, K, (B, L), generator=g, device="cuda")
+    smp = fb.DiffusionJumpySampler(s, lambda x, t, c: logits, K=K, T_train=200, T_infer=20, r=5, greedy=False,
+                                   device=torch.device("cuda"))
+    st = torch.tensor([7, 0], dtype=torch.int64, device="cuda")
+    smp.philox_state = st
+    cond = torch.zeros(B, 1, 1, device="cuda")
+    a, _ = smp._jump_once(x_t, 20, 5, cond, L)
+    assert int(st[1]) == 4
+    b, _ = smp._jump_once(x_t, 20, 5, cond, L)
+    assert int(st[1]) == 8
+    assert float((a != b).float().mean()) > 0.5                   # flat posterior over 4000 ids: almost all differ
+    st[1] = 0
+    c, _ = smp._jump_once(x_t, 20, 5, cond, L)
+    assert torch.equal(a, c)                                      # same state -> same draw (replayable)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -80,9 +80,21 @@ class _LfdLossFn(torch.autograd.Function):
         B, T, D = z_a.shape
         dev = z_a.device
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        G = torch.empty(D * D, dtype=torch.float32, device=dev)
-        L.check(L.lib.fddm_lfd_loss(op.cov.data_ptr(), D, float(B * T * op.world), op.lam, op.ws.data_ptr(),
-                                    loss.data_ptr(), G.data_ptr(), L.stream_ptr(dev)), "lfd_loss")
+        dv = op.d_valid
+        if dv == D:
+            G = torch.empty(D * D, dtype=torch.float32, device=dev)
+            L.check(L.lib.fddm_lfd_loss(op.cov.data_ptr(), D, float(B * T * op.world), op.lam, op.ws.data_ptr(),
+                                        loss.data_ptr(), G.data_ptr(), L.stream_ptr(dev)), "lfd_loss")
+        else:
+            # D was padded to a multiple of 8 for the tensor-core contraction: the loss and dloss/dC are taken over
+            # the leading d_valid x d_valid block only; the padded columns have z~ = 0 and a zero row/column of G
+            cov_v = op.cov[:D * D].view(D, D)[:dv, :dv].contiguous()
+            G_v = torch.empty(dv * dv, dtype=torch.float32, device=dev)
+            L.check(L.lib.fddm_lfd_loss(cov_v.data_ptr(), dv, float(B * T * op.world), op.lam, op.ws.data_ptr(),
+                                        loss.data_ptr(), G_v.data_ptr(), L.stream_ptr(dev)), "lfd_loss")
+            G = torch.zeros(D, D, dtype=torch.float32, device=dev)
+            G[:dv, :dv] = G_v.view(dv, dv)
+            G = G.view(-1)
         ctx.save_for_backward(z_a, z_b, op.sums, G, op.ws)
         ctx.meta = (B, T, D, op.dt, op.world, op.eps, op.group, op.private_ws)
         return loss.to(z_a.dtype)                              # the reference's result has the input dtype
@@ -128,6 +140,14 @@ class LfdPipeline:
         self.dt = L.dtype_code(z_a)
         if z_b.dtype != z_a.dtype:
             z_b = z_b.to(z_a.dtype)
+        # the reference accepts any D (losses:29-58); the contraction wants D % 8 == 0, so other widths are
+        # zero-padded (a differentiable torch pad: the gradient is sliced back automatically)
+        self.d_valid = D
+        if D % 8:
+            pad = 8 - D % 8
+            z_a = torch.nn.functional.pad(z_a, (0, pad))
+            z_b = torch.nn.functional.pad(z_b, (0, pad))
+            D += pad
         self.z_a, self.z_b = z_a.contiguous(), z_b.contiguous()
         self.lam, self.eps, self.group = float(lambda_offdiag), float(eps), group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
@@ -135,6 +155,8 @@ class LfdPipeline:
         self.shape = (B, T, D)
         nbytes = int(L.lib.fddm_lfd_workspace_bytes(B, T, D))
         self.private_ws = torch.is_grad_enabled() and (z_a.requires_grad or z_b.requires_grad)
+        if self.d_valid != D and self.world > 1:
+            raise ValueError("lfd_loss: D must be a multiple of 8 when the batch is sharded over ranks")
         if self.private_ws:
             # a workspace of its own, kept until backward: the packed tensor-core operand planes and the
             # standardisation tables written by the forward are reused by the backward contractions

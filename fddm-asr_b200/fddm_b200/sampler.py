@@ -60,6 +60,22 @@ class DiffusionJumpySampler:
         # generator state; every sampling jump advances the offset on the device (a captured add), which
         # makes a jump -- or a whole chain -- replayable in a CUDA graph with fresh noise per replay
         self.philox_state: Optional[torch.Tensor] = None
+        self._graph_enabled = False
+        self._graphs = {}
+
+    def enable_cuda_graph(self, enabled: bool = True) -> "DiffusionJumpySampler":
+        """capture the whole jump chain of `sample()` -- every decoder forward, coefficient
+        kernel and fused jump kernel -- in ONE CUDA graph per (cond shape, seq_len) and replay it on later calls.
+        Nothing in the chain synchronises with the host, so the replay removes the per-jump launch and Python
+        overhead that dominates at small batch (the reference's evaluation builds a sampler per utterance, B=1:
+        models/evaluate.py:165-174).  Requirements: the decoder must be CUDA-graph capturable; the returned
+        tensors are the graph's static outputs and are overwritten by the next `sample()` with the same shapes
+        (clone them to keep them).  Sampling draws use the device-side Philox state, advanced inside the graph,
+        so every replay draws fresh noise."""
+        self._graph_enabled = bool(enabled)
+        if not enabled:
+            self._graphs = {}
+        return self
 
     # sampler:219-236, including the 0-based table indexed by a 1-based train-axis index (Q3)
     def _alpha_bar_index(self, t_infer_scalar: int) -> int:
@@ -162,6 +178,44 @@ class DiffusionJumpySampler:
         """sampler:241-293.  Returns (x_0 ids [B,L], p_x0_last [B,L,K]).
         `x_init` (extra, keyword-only): the initial ids x_T instead of drawing them here (parity tests,
         CUDA-graph replay with caller-owned state)."""
+        if self._graph_enabled and cond_c.is_cuda and not torch.cuda.is_current_stream_capturing():
+            return self._sample_graphed(cond_c, seq_len, x_init)
+        return self._sample_chain(cond_c, seq_len, x_init)
+
+    @torch.no_grad()
+    def _sample_graphed(self, cond_c: Tensor, seq_len: int, x_init: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+        B = cond_c.size(0)
+        dev = cond_c.device
+        key = (tuple(cond_c.shape), cond_c.dtype, int(seq_len), dev.index)
+        # x_T is drawn outside the graph (one tiny kernel, same generator semantics as the eager path)
+        x_T = x_init.long() if x_init is not None else torch.randint(low=0, high=self.K, size=(B, seq_len), device=dev,
+                                                                      generator=self.generator)
+        ent = self._graphs.get(key)
+        if ent is None:
+            sampling = (self.posterior_mode != "max") and (not self.greedy)
+            if sampling and self.noise_fn is None and self.philox_state is None:
+                seed, _ = philox_seed_offset(dev, self.generator, 4)
+                self.philox_state = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+            s_cond = cond_c.clone()
+            s_x = x_T.clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                         # warm-up outside capture (lazy init, autotune)
+                for _ in range(2):
+                    self._sample_chain(s_cond, seq_len, s_x)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._sample_chain(s_cond, seq_len, s_x)
+            ent = self._graphs[key] = (graph, s_cond, s_x, out)
+        graph, s_cond, s_x, out = ent
+        s_cond.copy_(cond_c)
+        s_x.copy_(x_T)
+        graph.replay()
+        return out
+
+    @torch.no_grad()
+    def _sample_chain(self, cond_c: Tensor, seq_len: int, x_init: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
         B = cond_c.size(0)
         device = cond_c.device
         if x_init is not None:

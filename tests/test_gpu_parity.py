@@ -494,6 +494,43 @@ def test_jump_fast_flavour_target_distribution_vs_oracle(fb, mode, io, B, L, K):
         assert (np.take_along_axis(want, idn[..., None], -1) > 0).all()
 
 
+@pytest.mark.parametrize("greedy", [True, False])
+def test_sampler_cuda_graph_chain(fb, greedy):
+    """the whole jump chain captured in one CUDA graph gives the same ids as the eager chain
+    (greedy: bit-equal; sampling: equal given the same device-side Philox state) and fewer host launches."""
+    K, B, L = 4000, 2, 24
+    s = make_sched(fb, K, 200)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    W = torch.randn(4, B, L, K, generator=g, device="cuda") * 3
+
+    class Dec:                                                     # graph-capturable stand-in: logits depend on x and t
+        def __call__(self, x, t, c):
+            return W[(t[0] // 5 - 1).clamp(0, 3)] + 0.01 * (x % 7).unsqueeze(-1).float() + c.sum() * 0.0
+
+    mk = lambda: fb.DiffusionJumpySampler(s, Dec(), K=K, T_train=200, T_infer=20, r=5, greedy=greedy,
+                                          device=torch.device("cuda"))
+    cond = torch.randn(B, 3, 5, device="cuda")
+    x_T = torch.randint(0, K, (B, L), device="cuda")
+    eager = mk()
+    eager.philox_state = torch.tensor([11, 0], dtype=torch.int64, device="cuda")
+    want_x0, want_p = eager.sample(cond, L, x_init=x_T)
+    graphed = mk().enable_cuda_graph()
+    graphed.philox_state = torch.tensor([11, 0], dtype=torch.int64, device="cuda")
+    n0 = fb._lib.launch_count()
+    got_x0, got_p = graphed.sample(cond, L, x_init=x_T)            # captures (2 warm-ups + capture) and replays
+    graphed.philox_state[1] = 0
+    n1 = fb._lib.launch_count()
+    got_x0, got_p = [v.clone() for v in graphed.sample(cond, L, x_init=x_T)]   # pure replay: no library call on the host
+    assert fb._lib.launch_count() == n1 and n1 > n0
+    assert torch.equal(got_x0, want_x0)
+    assert torch.equal(got_p, want_p)
+    assert torch.equal(graphed.last_resampled_idx, eager.last_resampled_idx)
+    if not greedy:                                                 # the offset keeps advancing across replays: fresh noise
+        a = graphed.last_resampled_idx.clone()
+        graphed.sample(cond, L, x_init=x_T)
+        assert not torch.equal(a, graphed.last_resampled_idx)
+
+
 def test_jump_philox_offsets_advance_per_jump(fb):
     """Two consecutive sampling jumps driven by one device-side {seed, offset} draw DIFFERENT variates (the
     offset is advanced on the device after every jump), and a sample_q call sharing that state is independent
@@ -556,6 +593,75 @@ def test_lfd_vs_oracle(fb, io, B, T, D, rho):
     gtol = 2e-5 if io == "f32" else HALF_TOL
     assert rel_err(a.grad.float().cpu().numpy(), 3.0 * ga) < gtol
     assert rel_err(b.grad.float().cpu().numpy(), 3.0 * gb) < gtol
+
+
+@pytest.mark.parametrize("B,T,D", [(8, 5, 20), (40, 3, 12), (4, 7, 6)])
+def test_lfd_any_width(fb, B, T, D):
+    """The reference accepts any feature width (losses:29-58); widths that are not a multiple of 8 go through the
+    zero-padded path and must give the same loss and gradients."""
+    rng = np.random.default_rng(D)
+    za = rng.normal(size=(B, T, D)).astype(np.float32)
+    zb = (0.7 * za + 0.7 * rng.normal(size=(B, T, D))).astype(np.float32)
+    want, ga, gb = O.lfd_loss(za, zb, 5e-3, dtype=np.float64, want_grad=True)
+    a = dev(za).requires_grad_(True); b = dev(zb).requires_grad_(True)
+    loss = fb.lfd_loss(a, b, 5e-3)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(want)) <= FP32_TOL * abs(float(want))
+    assert a.grad.shape == (B, T, D)
+    assert rel_err(a.grad.cpu().numpy(), ga) < 2e-5 and rel_err(b.grad.cpu().numpy(), gb) < 2e-5
+
+
+def test_kl_float_mask_is_a_weight(fb):
+    """train.py:250 multiplies by x_mask.float(): a non-boolean mask weights the tokens."""
+    rng = np.random.default_rng(5)
+    B, L, V, T = 4, 16, 4000, 200
+    s = make_sched(fb, V, T)
+    ad = fb.SchedulerAdapter(s)
+    logits = (rng.normal(size=(B, L, V)) * 2).astype(np.float32)
+    x0 = rng.integers(0, V, size=(B, L)); xt = rng.integers(0, V, size=(B, L)); t = rng.integers(1, T + 1, size=B)
+    w = rng.random((B, L)).astype(np.float32)
+    w[0, :5] = 0.0; w[1] = 0.0                                    # zero weights and an all-zero sample (Q6)
+    tok, grad = O.kl_token_terms(xt, x0, logits, t, s.betas.cpu().numpy(), dtype=np.float64, want_grad=True)
+    per = (tok * w).sum(1) / (w.sum(1) + 1e-8)
+    want = per.mean()
+    wgrad = grad * (w / (w.sum(1, keepdims=True) + 1e-8) / B)[..., None]
+    lg = dev(logits).requires_grad_(True)
+    loss = ad.kl_term(dev(xt), dev(x0), lg, dev(t), dev(w))
+    loss.backward()
+    assert abs(float(loss.detach()) - want) <= FP32_TOL * abs(want)
+    assert rel_err(lg.grad.cpu().numpy(), wgrad) < FP32_TOL
+    # a 0/1 float mask equals the boolean mask
+    m = rng.random((B, L)) < 0.6
+    with torch.no_grad():
+        l_b = ad.kl_term(dev(xt), dev(x0), dev(logits), dev(t), dev(m))
+        l_f = ad.kl_term(dev(xt), dev(x0), dev(logits), dev(t), dev(m.astype(np.float32)))
+    assert float(l_b) == float(l_f)
+
+
+def test_out_of_range_t_is_a_device_side_assert():
+    """The reference indexes betas[t-1]: t outside 1..T is an error there (IndexError on CPU, device-side
+    assert on CUDA).  Here: an asynchronous device-side assert (no host sync on the hot path).  Run in a
+    subprocess because a device-side assert poisons the CUDA context."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, r'{os.path.join(root, 'fddm-asr_b200')}')\n"
+        "import fddm_b200 as fb\n"
+        "s = fb.DiscreteDiffusionScheduler(K=64, T=10, device=torch.device('cuda'))\n"
+        "ad = fb.SchedulerAdapter(s)\n"
+        "x = torch.zeros(2, 3, dtype=torch.long, device='cuda')\n"
+        "lg = torch.zeros(2, 3, 64, device='cuda')\n"
+        "try:\n"
+        "    ad.kl_term(x, x, lg, torch.tensor([1, 11], device='cuda'))\n"
+        "    torch.cuda.synchronize()\n"
+        "except Exception as e:\n"
+        "    print('RAISED', type(e).__name__); sys.exit(0)\n"
+        "print('NO ERROR'); sys.exit(1)\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "RAISED" in out.stdout, (out.stdout[-500:], out.stderr[-1500:])
 
 
 def test_lfd_shape_assert(fb):

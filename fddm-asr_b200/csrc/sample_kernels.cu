@@ -329,6 +329,10 @@ __device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, con
   }
   if (c.identity) {                                              // sched:133-134 (delta <= 0)
     if (threadIdx.x == 0) *x_out_row = c.xt;
+    if (p.flags & FDDM_JUMP_DEBUG_W) {
+      T* w_row = static_cast<T*>(p.p_out) + static_cast<size_t>(x_out_row - p.x_out) * p.K;
+      row.store(w_row, [&](int k, float) { return k == c.xt ? 1.0f : 0.0f; });
+    }
     return;
   }
 
@@ -355,6 +359,14 @@ __device__ __forceinline__ void jump_row_fast(Row& row, const JumpParams& p, con
     if (w == (owner >> 5)) mw += corr;
     tot += fmaxf(mw, 0.0f);
     cw[w] = tot;
+  }
+  if (p.flags & FDDM_JUMP_DEBUG_W) {                            // test hook: the normalised target distribution
+    T* w_row = static_cast<T*>(p.p_out) + static_cast<size_t>(x_out_row - p.x_out) * p.K;
+    const float inv_tot = 1.0f / tot;
+    row.store(w_row, [&](int k, float x) {
+      const float pk = x * rs;
+      return fmaxf((k == c.xt) ? fmaf(wa_x, pk, wb_x) : fmaf(wa, pk, wb), 0.0f) * inv_tot;
+    });
   }
   const float t1 = tot * ((static_cast<float>(c.r0 >> 8) + 0.5f) * k2m24);
   int wsel = NW - 1;

@@ -84,21 +84,21 @@ def test_kl_fullsize_properties(fb, B, L, V, dtype):
     assert np.abs(got - want).max() <= gtol * np.abs(want).max()
 
 
-def port_kl_fp64(xt, x0, logits, t, betas, mask, chunk=8):
+def port_kl(xt, x0, logits, t, betas, mask, dtype, chunk=8):
     """KL loss and d loss / d logits of the reference formula (train.py:190-255 as restated in
-    oracle/fddm_torch_port.py) in fp64 on the GPU, over the whole batch, evaluated in batch chunks (the loss is
-    a mean of per-sample terms).  Half-precision logits: softmax in the logits dtype first (quirk Q11)."""
+    oracle/fddm_torch_port.py) on the GPU in `dtype` (fp64: the checker; fp32: the reference's own arithmetic),
+    over the whole batch, evaluated in batch chunks (the loss is a mean of per-sample terms)."""
     B = logits.shape[0]
-    b64 = betas.double()
+    bt = betas.to(dtype)
     total = 0.0
     grads = []
     for i in range(0, B, chunk):
         sl = slice(i, min(B, i + chunk))
-        lg = logits[sl].double().requires_grad_(True)
-        part = P.kl_term(xt[sl], x0[sl], lg, t[sl], b64, mask[sl]) * ((sl.stop - sl.start) / B)
+        lg = logits[sl].to(dtype).requires_grad_(True)
+        part = P.kl_term(xt[sl], x0[sl], lg, t[sl], bt, mask[sl]) * ((sl.stop - sl.start) / B)
         part.backward()
         total += float(part.detach())
-        grads.append(lg.grad)
+        grads.append(lg.grad.double())
     return total, torch.cat(grads, 0)
 
 
@@ -109,7 +109,10 @@ def port_kl_fp64(xt, x0, logits, t, betas, mask, chunk=8):
                                              ("c2", 32, 128, 8000, torch.bfloat16)])
 def test_kl_fullsize_vs_port_fp64(fb, tag, B, L, V, dtype):
     """Whole-tensor check of the fused KL kernel (loss AND every gradient entry) against the fp64 port at
-    the full BASELINE sizes: 1e-5 relative in fp32, 1e-2 with bf16 logits (north_star bars)."""
+    the full BASELINE sizes: 1e-5 relative in fp32, 1e-2 with bf16 logits (north_star bars), in the max norm
+    over the tensor.  Row by row (each row against ITS OWN largest entry) the kernel must additionally be as
+    close to fp64 as the reference's own fp32 arithmetic is on that row: rows whose gradient is a cancellation
+    residue (t <= 2, or a tiny posterior mismatch) are ill-conditioned in fp32 for the reference too."""
     s = sched(fb, V)
     ad = fb.SchedulerAdapter(s)
     logits, x0, mask, t = synth(B, L, V, dtype)
@@ -117,20 +120,18 @@ def test_kl_fullsize_vs_port_fp64(fb, tag, B, L, V, dtype):
     lg = logits.clone().requires_grad_(True)
     loss = ad.kl_term(xt, x0, lg, t, mask)
     loss.backward()
-    want, wgrad = port_kl_fp64(xt, x0, logits, t, s.betas, mask)
+    want, wgrad = port_kl(xt, x0, logits, t, s.betas, mask, torch.float64)
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     assert abs(float(loss.detach()) - want) <= tol * abs(want), (float(loss.detach()), want)
     err = float((lg.grad.double() - wgrad).abs().max()) / float(wgrad.abs().max())
     assert err <= tol, err
-    # per-row check as well (a max-norm over the tensor is dominated by the large-gradient rows): every row
-    # within tol of ITS OWN largest entry, except rows of the t <= 2 samples where the unmodified reference in
-    # fp32 is itself 1.8e-4 away from fp64 -- those get that documented bar
-    rerr = (lg.grad.double() - wgrad).abs().amax(-1) / wgrad.abs().amax(-1).clamp_min(1e-300)
-    small_t = (t <= 2)[:, None].expand(B, L)
-    ok_rows = mask & ~small_t
-    assert float(rerr[ok_rows].max()) <= (2e-5 if dtype == torch.float32 else 2e-2), float(rerr[ok_rows].max())
-    if bool((mask & small_t).any()):
-        assert float(rerr[mask & small_t].max()) <= (6e-4 if dtype == torch.float32 else 2e-2)
+    ref32_loss, ref32_grad = port_kl(xt, x0, logits.float(), t, s.betas, mask, torch.float32)
+    rmax = wgrad.abs().amax(-1).clamp_min(1e-300)
+    ours = (lg.grad.double() - wgrad).abs().amax(-1) / rmax
+    ref = (ref32_grad - wgrad).abs().amax(-1) / rmax
+    bar = torch.maximum(torch.full_like(ref, 2 * tol), 4.0 * ref)
+    worst = (ours / bar)[mask]
+    assert float(worst.max()) <= 1.0, (float(worst.max()), float(ours[mask].max()), float(ref[mask].max()))
 
 
 @pytest.mark.parametrize("mode", ["exact", "fast"])

@@ -505,7 +505,8 @@ def test_sampler_cuda_graph_chain(fb, greedy):
 
     class Dec:                                                     # graph-capturable stand-in: logits depend on x and t
         def __call__(self, x, t, c):
-            return W[(t[0] // 5 - 1).clamp(0, 3)] + 0.01 * (x % 7).unsqueeze(-1).float() + c.sum() * 0.0
+            step = (t[:1] // 5 - 1).clamp(0, 3)                     # (no 0-dim tensor index: that would sync)
+            return torch.index_select(W, 0, step)[0] + 0.01 * (x % 7).unsqueeze(-1).float() + c.sum() * 0.0
 
     mk = lambda: fb.DiffusionJumpySampler(s, Dec(), K=K, T_train=200, T_infer=20, r=5, greedy=greedy,
                                           device=torch.device("cuda"))
@@ -540,8 +541,9 @@ def test_jump_philox_offsets_advance_per_jump(fb):
     g = torch.Generator(device="cuda").manual_seed(1)
     logits = torch.randn(B, L, K, generator=g, device="cuda")
     x_t = torch.randint(0, K, (B, L), generator=g, device="cuda")
+    # fast mode at t=20 -> t'=15: alpha-bar is tiny there, the target is almost uniform over the 4000 ids
     smp = fb.DiffusionJumpySampler(s, lambda x, t, c: logits, K=K, T_train=200, T_infer=20, r=5, greedy=False,
-                                   device=torch.device("cuda"))
+                                   sampling_mode="fast", device=torch.device("cuda"))
     st = torch.tensor([7, 0], dtype=torch.int64, device="cuda")
     smp.philox_state = st
     cond = torch.zeros(B, 1, 1, device="cuda")
@@ -549,7 +551,7 @@ def test_jump_philox_offsets_advance_per_jump(fb):
     assert int(st[1]) == 4
     b, _ = smp._jump_once(x_t, 20, 5, cond, L)
     assert int(st[1]) == 8
-    assert float((a != b).float().mean()) > 0.5                   # flat posterior over 4000 ids: almost all differ
+    assert float((a != b).float().mean()) > 0.9                   # near-uniform target over 4000 ids: almost all differ
     st[1] = 0
     c, _ = smp._jump_once(x_t, 20, 5, cond, L)
     assert torch.equal(a, c)                                      # same state -> same draw (replayable)

@@ -225,7 +225,9 @@ struct JumpParams {
   int64_t* x_out;
   int64_t* argmax_p_out;     // optional: argmax_k p_x0 (the sampler's final x_0, sampler:292)
   void* p_out;
-  unsigned int* work;        // dynamic row counter (self-resetting pair: next, done)
+  unsigned int* work;        // self-resetting counters: [0] next row, [1] CTAs done, [2] rows on the fallback list
+  int* row_list;             // fallback list (greedy streamed kernel -> bit-faithful kernel), [rows] ints after the counters
+  int list_mode;             // 1: rows are row_list[0 .. work[2]) instead of 0 .. rows
   int B, L, K, rows;
   int flags;
   int abar_index;
@@ -624,6 +626,7 @@ __device__ __forceinline__ void jump_epilogue(const JumpParams& p, int tid) {
     if (d == gridDim.x - 1) {
       p.work[0] = 0;
       p.work[1] = 0;
+      if (p.list_mode) p.work[2] = 0;            // the list has been consumed
       __threadfence();
     }
   }
@@ -660,12 +663,14 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
       uint32_t round = 0;
       for (;;) {
         if (round > 0) mbar_wait_backoff(&ring.empty[s], (round - 1) & 1);
-        const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
-        if (row >= p.rows) {
+        int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
+        const int bound = p.list_mode ? static_cast<int>(__ldcg(&p.work[2])) : p.rows;
+        if (row >= bound) {
           ring.meta[s].row = -1;
           mbar_arrive(&ring.full[s]);
           break;
         }
+        if (p.list_mode) row = __ldcg(&p.row_list[row]);
         // the copies go out first; the row's metadata (and its random bits) are prepared under their latency;
         // the stage becomes visible to the consumers only with the arrive at the end
         mbar_expect_tx(&ring.full[s], row_bytes + (NOISE == 1 ? noise_bytes : 0u));
@@ -1030,6 +1035,226 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
   jump_epilogue<NT>(p, tid);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Greedy / posterior_mode == "max" production kernel ("streamed", the reference's default inference
+// configuration: configs/fddm_zhTW_base.yaml greedy: true).  argmax_k of the target distribution decides the id,
+// and the target is monotone in p_k for every k != x_t, so the decision needs: the row's largest logit, whether
+// it is CLEARLY the largest (no other logit within eps_z of it), and -- exact mode -- the one comparison with
+// the entry x_t, whose coefficient differs.  All of that is exact-arithmetic-free: a row is decided here only
+// when its margin exceeds, by an order of magnitude, every approximation made (MUFU exp / reciprocal, the
+// summation order of S, sum(p) = 1) AND the reference's own rounding; then the id equals the reference's id
+// bit for bit.  Rows that are not clear (near-ties, degenerate coefficients) are appended to a list and
+// re-done by the bit-faithful register-resident kernel (libm expf, IEEE division, the reference's op order),
+// which also rewrites their p_x0 / argmax outputs.  Same shape as jump_rows_streamed_kernel: the row stays in
+// the stage, two passes, one block barrier, 6 CTAs/SM.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct GreedyMargins;
+template <> struct GreedyMargins<float> { static constexpr float eps_z = 2.0e-3f, rel = 2.0e-5f; };
+template <> struct GreedyMargins<__nv_bfloat16> { static constexpr float eps_z = 4.0e-2f, rel = 1.6e-2f; };
+template <> struct GreedyMargins<__half> { static constexpr float eps_z = 6.0e-3f, rel = 2.0e-3f; };
+
+template <typename T, int NT, int CTAS>
+__global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_greedy_streamed_kernel(const JumpParams p) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ uint64_t s_full, s_empty;
+  __shared__ RingMeta s_meta;
+  __shared__ float s_red[kRedFloats];
+  constexpr int N = Vec16<T>::N, NW = NT / 32;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float kEpsZ = GreedyMargins<T>::eps_z, kRel = GreedyMargins<T>::rel;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&s_full, 1);
+    mbar_init(&s_empty, NW);
+    mbar_fence_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  const uint32_t row_bytes = static_cast<uint32_t>(p.K) * sizeof(T);
+  const bool exact = (p.flags & FDDM_JUMP_EXACT) != 0;
+
+  if (tid >= NT) {
+    if (tid == NT) {                       // producer lane
+      for (uint32_t it = 0;; ++it) {
+        if (it > 0) mbar_wait_backoff(&s_empty, (it - 1) & 1);
+        const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
+        if (row >= p.rows) {
+          s_meta.row = -1;
+          mbar_arrive(&s_full);
+          break;
+        }
+        mbar_expect_tx(&s_full, row_bytes);
+        tma_load_1d(dyn_smem, static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes, row_bytes,
+                    &s_full);
+        JumpRowCtx c;
+        jump_load_ctx(p, row, c);
+        RingMeta mt;
+        mt.row = row; mt.w = c.identity ? 0.0f : 1.0f; mt.i0 = c.xt; mt.i1 = 0;
+        mt.f0 = exact ? c.a_c : c.ab;
+        mt.f1 = c.b_c; mt.f2 = c.a_g; mt.f3 = c.b_g;
+        mt.r0 = mt.r1 = mt.r2 = 0u;
+        s_meta = mt;
+        mbar_arrive(&s_full);
+      }
+    }
+    return;
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nvec = p.K / N;
+  RedRing red{s_red, 0};
+  const uint4* sv = reinterpret_cast<const uint4*>(dyn_smem);
+  const bool need_p = (p.flags & FDDM_JUMP_WRITE_P) != 0 || p.argmax_p_out != nullptr;
+  const float c_thr = ex2_approx(-kEpsZ * kLog2e);        // e_k >= c_thr  <=>  z_k >= m_t - eps_z
+
+  for (uint32_t it = 0;; ++it) {
+    mbar_wait(&s_full, it & 1);
+    const RingMeta mt = s_meta;
+    if (mt.row < 0) break;
+    const int xt = mt.i0;
+    // pass 1: thread max
+    float mx[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      float f[N];
+      Vec16<T>::unpack(sv[vi], f);
+#pragma unroll
+      for (int e = 0; e < N; ++e) mx[e & 3] = fmaxf(mx[e & 3], f[e]);
+    }
+    const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    // pass 2: thread sum of exp(z - m_t) and the number of entries within eps_z of the thread max
+    const float nm_t = -m_t * kLog2e;
+    float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    int cnt_t = 0;
+#pragma unroll 4
+    for (int vi = tid; vi < nvec; vi += NT) {
+      float f[N];
+      Vec16<T>::unpack(sv[vi], f);
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float ek = ex2_approx(fmaf(f[e], kLog2e, nm_t));
+        sx[e & 3] += ek;
+        cnt_t += (ek >= c_thr) ? 1 : 0;
+      }
+    }
+    const float s_t = (sx[0] + sx[1]) + (sx[2] + sx[3]);
+    const float z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(dyn_smem) + xt);
+    if (!need_p) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty);
+    }
+    // warp: max, rescaled sum, contenders (conservative: counted against the thread maxima), owner lane of the max
+    float m_w = m_t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, o));
+    float s_w = s_t * ex2_approx((m_t - m_w) * kLog2e);
+    int cnt_w = (m_t >= m_w - kEpsZ) ? cnt_t : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_w += __shfl_xor_sync(0xffffffffu, s_w, o);
+      cnt_w += __shfl_xor_sync(0xffffffffu, cnt_w, o);
+    }
+    const unsigned own = __ballot_sync(0xffffffffu, m_t == m_w);
+    float* sc = red.next();
+    if (lane == 0) {
+      sc[warp] = m_w; sc[32 + warp] = s_w;
+      sc[64 + warp] = __int_as_float(cnt_w); sc[96 + warp] = __int_as_float(__ffs(own) - 1);
+    }
+    consumer_sync<NT>();
+    float m = sc[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = fmaxf(m, sc[w]);
+    float S = 0.0f;
+    int contenders = 0, wmax = -1;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      S += sc[32 + w] * ex2_approx((sc[w] - m) * kLog2e);
+      if (sc[w] >= m - kEpsZ) contenders += __float_as_int(sc[64 + w]);
+      if (wmax < 0 && sc[w] == m) wmax = w;
+    }
+    const int lmax = __float_as_int(sc[96 + wmax]);
+    const float inv_S = rcp_approx(S);
+    const float nm = -m * kLog2e;
+
+    if (need_p) {                          // p_x0 in the logits dtype (Q11); its argmax is the clear top entry
+      T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K : nullptr;
+      if (p_row) {
+#pragma unroll 2
+        for (int vi = tid; vi < nvec; vi += NT) {
+          float f[N];
+          Vec16<T>::unpack(sv[vi], f);
+#pragma unroll
+          for (int e = 0; e < N; ++e) f[e] = Vec16<T>::round_trip(ex2_approx(fmaf(f[e], kLog2e, nm)) * inv_S);
+          stg_stream_v4(reinterpret_cast<uint4*>(p_row) + vi, Vec16<T>::pack(f));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty);
+    }
+
+    // ---- the decision (every thread evaluates it; the owner warp acts on it) ----
+    const float p1 = inv_S;                                   // the largest probability: exp(0) / S
+    const float pxt = ex2_approx(fmaf(z_xt, kLog2e, nm)) * inv_S;
+    bool clear = contenders == 1;
+    bool pick_xt = false;
+    if (mt.w == 0.0f) {                                       // sched:133-134 (delta <= 0): identity
+      pick_xt = true;
+      clear = clear || !need_p;                               // the id is x_t regardless; argmax p still needs a clear top
+    } else if (exact) {
+      const float a_c = mt.f0, b_c = mt.f1, a_g = mt.f2, b_g = mt.f3;
+      const float A_gen = b_c, A_xt = a_c + b_c;
+      const float v1 = A_gen * fmaf(a_g, p1, b_g), vx = A_xt * fmaf(a_g, pxt, b_g);
+      const bool top_is_xt = (z_xt == m);
+      // a probability margin of eps_z must translate into a value margin of kRel: (a_g p1) / (a_g p1 + b_g) * eps_z >= kRel
+      clear = clear && b_c > 0.0f && a_g > 0.0f && (a_g * p1 * kEpsZ * 0.5f >= kRel * fmaf(a_g, p1, b_g));
+      if (top_is_xt) {
+        pick_xt = true;
+        clear = clear && (a_c >= 8.0f * kRel * A_xt);
+      } else {
+        pick_xt = vx > v1;
+        clear = clear && (fabsf(vx - v1) > 8.0f * kRel * fmaxf(vx, v1));
+      }
+    } else {
+      const float ab = mt.f0, mixu = (1.0f - ab) * p.u;
+      clear = clear && ab > 0.0f && (ab * p1 * kEpsZ * 0.5f >= kRel * fmaf(ab, p1, mixu));
+    }
+    if (!clear) {
+      if (tid == 0) p.row_list[atomicAdd(&p.work[2], 1u)] = mt.row;   // re-done by the bit-faithful kernel
+      continue;
+    }
+    if (warp != wmax) continue;
+    // the owner warp finds the index of the row's (unique, clear) top entry among the owner lane's vectors,
+    // re-read from global memory (an L2 hit), one vector per lane
+    const int tid_top = (wmax << 5) + lmax;
+    const int nv_top = (nvec - tid_top + NT - 1) / NT;
+    const uint4* grow = reinterpret_cast<const uint4*>(static_cast<const T*>(p.logits) + static_cast<size_t>(mt.row) * p.K);
+    int k_top = -1;
+    for (int j0 = 0; j0 < nv_top && k_top < 0; j0 += 32) {
+      const int j = j0 + lane;
+      int found = -1;
+      if (j < nv_top) {
+        const int vi = j * NT + tid_top;
+        float f[N];
+        Vec16<T>::unpack(__ldg(grow + vi), f);
+#pragma unroll
+        for (int e = N - 1; e >= 0; --e)
+          if (f[e] == m) found = vi * N + e;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, found >= 0);
+      if (hit != 0u) k_top = __shfl_sync(0xffffffffu, found, __ffs(hit) - 1);
+    }
+    if (lane == 0) {
+      if (k_top < 0) {                                        // cannot happen; stay safe
+        p.row_list[atomicAdd(&p.work[2], 1u)] = mt.row;
+      } else {
+        p.x_out[mt.row] = pick_xt ? xt : k_top;
+        if (p.argmax_p_out) p.argmax_p_out[mt.row] = k_top;
+      }
+    }
+  }
+  jump_epilogue<NT>(p, tid);
+}
+
 // generic path
 template <typename T, int NT, int NOISE>
 __global__ void __launch_bounds__(NT, 1) jump_rows_generic_kernel(const JumpParams p) {
@@ -1104,6 +1329,36 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
       return FDDM_OK;
     }
   }
+  if (NOISE == 0 && aligned && p.K <= 32768 && p.work != nullptr && !p.list_mode && p.row_list != nullptr &&
+      getenv("FDDM_JUMP_CFG") == nullptr) {
+    // greedy streamed kernel; the rows it does not decide go through the bit-faithful kernel below (list mode)
+    const size_t stage = ((row_bytes + 127) & ~size_t(127)) + 128;
+    int ctas = static_cast<int>((216 * 1024) / (stage + 2048));
+    if (ctas >= 2) {
+      ctas = std::min(ctas, 6);
+      const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * ctas));
+      const int nvec = p.K / Vec16<T>::N;
+#define FDDM_JUMP_GREEDY(NT_, CTAS_)                                                                        \
+  do {                                                                                                      \
+    auto kfn = jump_rows_greedy_streamed_kernel<T, NT_, CTAS_>;                                             \
+    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage))); \
+    kfn<<<grid, NT_ + 32, stage, stream>>>(p);                                                              \
+  } while (0)
+      if (nvec <= 2048) {
+        if (ctas >= 6) FDDM_JUMP_GREEDY(128, 6);
+        else if (ctas >= 4) FDDM_JUMP_GREEDY(128, 4);
+        else FDDM_JUMP_GREEDY(128, 2);
+      } else {
+        if (ctas >= 4) FDDM_JUMP_GREEDY(256, 4);
+        else FDDM_JUMP_GREEDY(256, 2);
+      }
+#undef FDDM_JUMP_GREEDY
+      FDDM_LAUNCH_OK();
+      JumpParams q = p;
+      q.list_mode = 1;
+      return launch_jump<T, NOISE>(q, stream);
+    }
+  }
   if (aligned && p.K <= 32768 && p.work != nullptr) {
     // (consumer threads, row entries per thread, resident CTAs per SM).  The per-row fixed cost (reductions,
     // barrier, draw) is per THREAD, so the in-kernel-RNG flavour uses few threads with many entries each.
@@ -1126,6 +1381,9 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
       plan.smem_bytes = ((row_pad + noise_bytes + 127) & ~size_t(127)) * force_stages + 128;
     }
     if (plan.nstages >= 1) {
+      // (list mode: the number of listed rows is only known on the device -- it can be all of them, e.g. fast
+      //  mode at a noisy step where the uniform mix swamps every difference -- so the grid stays full; CTAs
+      //  that find the list empty leave at once)
       const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
       const uint32_t sb = static_cast<uint32_t>((row_pad + noise_bytes + 127) & ~size_t(127));
 #define FDDM_JUMP_LAUNCH(NT_, EPT_, CTAS_)                                                                  \
@@ -1179,6 +1437,11 @@ int FDDM_JUMP_FN(const JumpParams& p, int noise, cudaStream_t stream) {
 
 #ifndef FDDM_JUMP_DT
 extern "C" {
+
+size_t fddm_jump_workspace_bytes(int64_t B, int64_t L) {
+  if (B <= 0 || L <= 0) return 0;
+  return 128 + static_cast<size_t>(B) * static_cast<size_t>(L) * sizeof(int);   // counters + fallback row list
+}
 
 int fddm_sample_q_ids(const int64_t* x0, const int64_t* t, const float* alpha_bar, int64_t T, int64_t B, int64_t L,
                       int64_t K, float eps, const float* exp_noise, uint64_t seed, uint64_t offset,
@@ -1234,6 +1497,8 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
   p.logits = logits; p.x_t = x_t; p.coeffs = coeffs; p.alpha_bar = alpha_bar; p.noise = exp_noise;
   p.x_out = x_out; p.argmax_p_out = argmax_p_out; p.p_out = p_x0_out;
   p.work = static_cast<unsigned int*>(workspace);
+  p.row_list = workspace ? reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + 128) : nullptr;
+  p.list_mode = 0;
   p.B = static_cast<int>(B); p.L = static_cast<int>(L); p.K = static_cast<int>(K); p.rows = static_cast<int>(B * L);
   p.flags = flags; p.abar_index = static_cast<int>(abar_index);
   p.temperature = temperature; p.eps = eps;

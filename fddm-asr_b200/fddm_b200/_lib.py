@@ -21,7 +21,6 @@ LIB_PATH = os.environ.get("FDDM_B200_LIB") or os.path.join(os.path.dirname(_HERE
 
 F32, BF16, F16 = 0, 1, 2
 JUMP_EXACT, JUMP_SAMPLE, JUMP_WRITE_P, JUMP_DEBUG_W = 0x1, 0x2, 0x4, 0x8
-JUMP_WORKSPACE_BYTES = 128
 LFD_PLANES_VALID = 0x2
 MAX_VOCAB = 49152
 
@@ -54,6 +53,7 @@ SIGNATURES = {
     "fddm_kl_forward_backward": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _f64, _vp, _vp,
                                         _vp, _vp, _vp]),
     "fddm_scale_inplace": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp]),
+    "fddm_jump_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "fddm_jump_step": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _f32, _vp, _u64, _u64,
                               _vp, _vp, _vp, _vp, _vp, _vp]),
     "fddm_lfd_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64]),

@@ -160,7 +160,7 @@ class DiffusionJumpySampler:
             p_x0 = torch.empty_like(logits)                     # softmax output keeps the logits dtype
         amax = torch.empty_like(x_t) if want_argmax else None
         x_out = torch.empty_like(x_t)
-        ws = L.zeroed_workspace(dev, "jump", L.JUMP_WORKSPACE_BYTES)
+        ws = L.zeroed_workspace(dev, "jump", int(L.lib.fddm_jump_workspace_bytes(B, Lq)))
         L.check(L.lib.fddm_jump_step(logits.data_ptr(), dt, x_t.data_ptr(), L.ptr(coeffs), L.ptr(alpha_bar),
                                      abar_index, B, Lq, self.K, flags, self.temperature, eps, L.ptr(noise), seed,
                                      offset, L.ptr(self.philox_state if (sample and noise is None) else None),

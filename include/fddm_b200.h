@@ -160,11 +160,13 @@ int fddm_scale_inplace(void* x, int dtype, int64_t n, const float* num, const fl
  *   exp_noise    fp32 [B*L, K] Exp(1) variates (per-entry race, bit-faithful arithmetic) or NULL ->
  *                in-kernel Philox (seed, offset) or device {seed, offset} in philox_state: hierarchical
  *                exponential race, one variate per thread, MUFU arithmetic
- *   workspace    FDDM_JUMP_WORKSPACE_BYTES bytes, zero-initialised ONCE by the caller (row scheduler)
+ *   workspace    fddm_jump_workspace_bytes(B,L) bytes whose first 128 are zero-initialised ONCE by the caller
+ *                (self-resetting row scheduler counters; the rest is the list of rows the greedy fast kernel
+ *                hands to the bit-faithful kernel)
  *   argmax_p_out optional int64 [B,L]: argmax_k p_x0 -- the sampler's final x_0 (sampler:292), fused
  *                here so the last p_x0 is never re-read
  *   p_x0_out     [B,L,K] in the logits dtype when FDDM_JUMP_WRITE_P, else may be NULL */
-#define FDDM_JUMP_WORKSPACE_BYTES 128
+size_t fddm_jump_workspace_bytes(int64_t B, int64_t L);
 int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const float* coeffs,
                    const float* alpha_bar, int64_t abar_index, int64_t B, int64_t L, int64_t K,
                    int flags, float temperature, float eps, const float* exp_noise, uint64_t seed,

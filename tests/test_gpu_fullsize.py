@@ -130,7 +130,9 @@ def test_kl_fullsize_vs_port_fp64(fb, tag, B, L, V, dtype):
     # reference as well (measured at c2: the reference's own fp32 arithmetic is up to 8e-3 away from fp64 on
     # such rows, this kernel up to 9e-3, medians 5e-7 vs 2e-7).  The kernel's per-row error DISTRIBUTION must
     # be no worse than twice the reference-fp32 one at every quantile.
-    _, ref32_grad = port_kl(xt, x0, logits.float(), t, s.betas, mask, torch.float32)
+    # (the reference's own arithmetic = the logits dtype: fp32 for fp32 logits; with bf16 logits the reference does
+    #  its softmax in bf16, quirk Q11, and returns a bf16 gradient)
+    _, ref32_grad = port_kl(xt, x0, logits, t, s.betas, mask, dtype)
     rmax = wgrad.abs().amax(-1).clamp_min(1e-300)
     ours = ((lg.grad.double() - wgrad).abs().amax(-1) / rmax)[mask]
     ref = ((ref32_grad - wgrad).abs().amax(-1) / rmax)[mask]

@@ -1075,13 +1075,25 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_greedy_streamed_kerne
 
   if (tid >= NT) {
     if (tid == NT) {                       // producer lane
+      // fast mode at a noisy step: when the uniform mix swamps alpha-bar * p even for p = 1, no row can be
+      // clear (see the decision below); every row then goes straight to the bit-faithful kernel's list and
+      // nothing is loaded here
+      bool hopeless = false;
+      if (!exact) {
+        const float ab = (p.abar_index < 0) ? 1.0f : p.alpha_bar[p.abar_index];
+        hopeless = !(ab > 0.0f) || (ab * kEpsZ * 0.5f < kRel * (ab + (1.0f - ab) * p.u));
+      }
       for (uint32_t it = 0;; ++it) {
-        if (it > 0) mbar_wait_backoff(&s_empty, (it - 1) & 1);
+        if (it > 0 && !hopeless) mbar_wait_backoff(&s_empty, (it - 1) & 1);
         const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
         if (row >= p.rows) {
           s_meta.row = -1;
           mbar_arrive(&s_full);
           break;
+        }
+        if (hopeless) {
+          p.row_list[atomicAdd(&p.work[2], 1u)] = row;
+          continue;
         }
         mbar_expect_tx(&s_full, row_bytes);
         tma_load_1d(dyn_smem, static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes, row_bytes,

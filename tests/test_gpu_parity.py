@@ -666,6 +666,92 @@ def test_out_of_range_t_is_a_device_side_assert():
     assert "RAISED" in out.stdout, (out.stdout[-500:], out.stderr[-1500:])
 
 
+def test_back_to_back_launches_are_bit_stable(fb):
+    """compute-sanitizer is closed on the B200 pool, so the properties racecheck/synccheck would probe are
+    tested functionally: the kernels' self-resetting work counters, rotating reduction scratch and mbarrier rings
+    are reused by back-to-back launches on one stream (and by concurrent launches on two streams, each with its
+    own workspace), and every repetition must reproduce the first result bit for bit."""
+    K, B, L, T = 8000, 6, 40, 200
+    s = make_sched(fb, K, T)
+    ad = fb.SchedulerAdapter(s)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    logits = torch.randn(B, L, K, generator=g, device="cuda") * 2
+    x0 = torch.randint(0, K, (B, L), generator=g, device="cuda")
+    t = torch.randint(1, T + 1, (B,), generator=g, device="cuda")
+    mask = torch.rand(B, L, generator=g, device="cuda") < 0.7
+    xt = ad.sample_q(x0, t)
+    za = torch.randn(40, 6, 64, generator=g, device="cuda"); zb = 0.5 * za + torch.randn(40, 6, 64, generator=g, device="cuda")
+
+    def run():
+        lg = logits.clone().requires_grad_(True)
+        loss = ad.kl_term(xt, x0, lg, t, mask)
+        loss.backward()
+        smp = fb.DiffusionJumpySampler(s, lambda x, tt, c: logits, K=K, T_train=T, T_infer=20, r=5, greedy=False,
+                                       device=torch.device("cuda"))
+        smp.philox_state = torch.tensor([3, 0], dtype=torch.int64, device="cuda")
+        ids, _ = smp._jump_once(x0, 20, 5, torch.zeros(B, 1, 1, device="cuda"), L, want_p=False)
+        smp.greedy = True
+        gids, _ = smp._jump_once(x0, 20, 5, torch.zeros(B, 1, 1, device="cuda"), L, want_p=False)
+        a = za.clone().requires_grad_(True); b = zb.clone().requires_grad_(True)
+        lf = fb.lfd_loss(a, b, 5e-3)
+        lf.backward()
+        return [loss.detach().clone(), lg.grad, ids, gids, lf.detach().clone(), a.grad, b.grad]
+
+    first = run()
+    for _ in range(10):
+        again = run()
+        for x, y in zip(first, again):
+            assert torch.equal(x, y)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(3):
+        for st in (s1, s2):
+            with torch.cuda.stream(st):
+                outs.append(run())
+    torch.cuda.synchronize()
+    for again in outs:
+        for x, y in zip(first, again):
+            assert torch.equal(x, y)
+
+
+def test_dropin_launcher_rebinds_a_stub_train_module(tmp_path):
+    """fddm-asr_b200/dropin/launch.py against a stub of the reference checkout: the stub's `train.py` imports the
+    three module paths exactly like the reference's (train.py:43-52), defines its own `SchedulerAdapter`
+    (train.py:176) and, in main(), uses whatever those names are bound to -- after the launcher they must be the
+    B200 implementations, and one training-step's worth of calls must run on the GPU."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (tmp_path / "train.py").write_text(
+        "import torch\n"
+        "from fddm.sched.diffusion_scheduler import DiscreteDiffusionScheduler\n"
+        "from losses.fddm_losses import lfd_loss\n"
+        "from sampler.jumpy_sampler import DiffusionJumpySampler\n"
+        "class SchedulerAdapter:\n"
+        "    def __init__(self, scheduler):\n"
+        "        raise RuntimeError('the stub adapter must have been rebound')\n"
+        "def main():\n"
+        "    dev = torch.device('cuda')\n"
+        "    sch = DiscreteDiffusionScheduler(K=512, T=20, device=dev)\n"
+        "    ad = SchedulerAdapter(sch)\n"
+        "    x0 = torch.randint(0, 512, (2, 8), device=dev); t = torch.tensor([3, 17], device=dev)\n"
+        "    xt = ad.sample_q(x0, t)\n"
+        "    lg = torch.randn(2, 8, 512, device=dev, requires_grad=True)\n"
+        "    loss = ad.kl_term(xt, x0, lg, t, x0 != 0) + ad.w_t(t).mean() * lfd_loss(torch.randn(2, 8, 16, device=dev), torch.randn(2, 8, 16, device=dev))\n"
+        "    loss.backward()\n"
+        "    smp = DiffusionJumpySampler(sch, lambda x, tt, c: lg.detach(), K=512, T_train=20, T_infer=4, r=2, device=dev)\n"
+        "    ids, p = smp.sample(torch.zeros(2, 1, 1, device=dev), 8)\n"
+        "    mods = (type(sch).__module__, type(ad).__module__, lfd_loss.__module__, type(smp).__module__)\n"
+        "    assert all(m.startswith('fddm_b200.') for m in mods), mods\n"
+        "    assert torch.isfinite(loss) and lg.grad is not None and ids.shape == (2, 8)\n"
+        "    print('STUB TRAIN OK', mods)\n")
+    out = subprocess.run([sys.executable, os.path.join(root, "fddm-asr_b200", "dropin", "launch.py"), str(tmp_path), "train"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "STUB TRAIN OK" in out.stdout, (out.stdout[-800:], out.stderr[-2000:])
+
+
 def test_lfd_shape_assert(fb):
     with pytest.raises(AssertionError):
         fb.lfd_loss(torch.zeros(2, 3, 8, device="cuda"), torch.zeros(2, 3, 16, device="cuda"))

@@ -634,7 +634,7 @@ def run_gpu(args):
     except Exception:
         pass
     for e in kernels:
-        t = traffic_db.get(f"{e['kernel']}:{args.dtype}:V{V}")
+        t = traffic_db.get(f"{e['kernel']}:{args.dtype}:V{V}") or traffic_db.get(f"{e['kernel']}:{args.dtype}:D{D}")
         if t:                                                     # ncu --set full capture, scaled by rows to this launch
             e["traffic"] = round(t["bytes_per_row"] * rows, 0); e["traffic_source"] = t["source"]
     dom = next((e for e in kernels if "frac" in e), None)         # largest time share with a defined roofline

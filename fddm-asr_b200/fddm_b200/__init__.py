@@ -5,6 +5,7 @@ Host-side mirror of the reference's interfaces over libfddm_b200.so (include/fdd
   SchedulerAdapter            <- train.py:176-273
   lfd_loss                    <- losses/fddm_losses.py
   DiffusionJumpySampler, ModelAdapter <- sampler/jumpy_sampler.py
+  calculate_cer, calculate_wer (+ batch_*) <- models/evaluate.py:94-134
 There is no CPU path: importing needs the built shared library, ops need CUDA tensors.
 """
 from . import _lib
@@ -13,6 +14,7 @@ from .scheduler import DiscreteDiffusionScheduler
 from .adapter import SchedulerAdapter
 from .sampler import DiffusionJumpySampler, ModelAdapter
 from .losses import LfdPipeline, lfd_loss
+from .metrics import batch_cer, batch_wer, calculate_cer, calculate_wer
 
 __all__ = ["DiscreteDiffusionScheduler", "SchedulerAdapter", "DiffusionJumpySampler", "ModelAdapter", "lfd_loss", "LfdPipeline",
-           "_lib", "set_sm_reserve"]
+           "_lib", "set_sm_reserve", "calculate_cer", "calculate_wer", "batch_cer", "batch_wer"]

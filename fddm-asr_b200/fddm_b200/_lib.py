@@ -56,6 +56,8 @@ SIGNATURES = {
     "fddm_jump_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "fddm_jump_step": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _f32, _vp, _u64, _u64,
                               _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fddm_edit_distance_workspace_bytes": (C.c_size_t, [_i64, _i64]),
+    "fddm_edit_distance": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "fddm_lfd_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64]),
     "fddm_lfd_stats": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp]),
     "fddm_lfd_xcov": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _f64, _f32, _vp, _vp, _vp]),

@@ -218,6 +218,19 @@ int fddm_lfd_backward(const void* z_a, const void* z_b, int dtype, int64_t B, in
                       float* bn_sums, int64_t bn_parts, int phase, void* dz_a, void* dz_b,
                       fddm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * f4  calculate_cer / calculate_wer                                    models/evaluate.py:94-134
+ * Batched Levenshtein distance (unit costs) over integer symbol sequences: characters' code points for CER,
+ * word ids for WER.  All pairs of an evaluation set in one launch.
+ *   ref, hyp          int32 concatenated symbols            ref_off, hyp_off   int64 [n_pairs + 1] offsets
+ *   max_hyp_len       the longest hypothesis (sizes the workspace: fddm_edit_distance_workspace_bytes)
+ *   dist_out          int32 [n_pairs] edit distances (the rates are dist / len(ref) with the reference's
+ *                     empty-reference rules, applied by the host mirror) */
+size_t fddm_edit_distance_workspace_bytes(int64_t n_pairs, int64_t max_hyp_len);
+int fddm_edit_distance(const int32_t* ref, const int64_t* ref_off, const int32_t* hyp,
+                       const int64_t* hyp_off, int64_t n_pairs, int64_t max_hyp_len, void* workspace,
+                       int32_t* dist_out, fddm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

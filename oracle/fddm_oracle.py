@@ -455,3 +455,32 @@ def near_tie(scores_row: np.ndarray, i: int, j: int, ulps: float = 8.0) -> bool:
     a = float(scores_row[i]); b = float(scores_row[j])
     scale = max(abs(a), abs(b), 1e-45)
     return abs(a - b) <= ulps * scale * 2.0 ** -23
+
+
+# ---------------------------------------------------------------------------------------------
+# CER / WER (models/evaluate.py:94-134)
+# ---------------------------------------------------------------------------------------------
+def edit_distance(r, h) -> int:
+    """Levenshtein distance with unit costs between two sequences (the DP of evaluate.py:101-115)."""
+    n, m = len(r), len(h)
+    prev = list(range(m + 1))
+    for i in range(1, n + 1):
+        cur = [i] + [0] * m
+        for j in range(1, m + 1):
+            cost = 0 if r[i - 1] == h[j - 1] else 1
+            cur[j] = min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + cost)
+        prev = cur
+    return prev[m]
+
+
+def calculate_cer(ref: str, hyp: str) -> float:
+    """evaluate.py:94-118."""
+    if len(ref) == 0:
+        return 0.0 if len(hyp) == 0 else 1.0
+    return float(edit_distance(list(ref), list(hyp))) / float(len(ref))
+
+
+def calculate_wer(ref: str, hyp: str) -> float:
+    """evaluate.py:120-134."""
+    r, h = ref.strip().split(), hyp.strip().split()
+    return 0.0 if len(r) == 0 else float(edit_distance(r, h)) / float(len(r))

@@ -752,6 +752,28 @@ def test_dropin_launcher_rebinds_a_stub_train_module(tmp_path):
     assert out.returncode == 0 and "STUB TRAIN OK" in out.stdout, (out.stdout[-800:], out.stderr[-2000:])
 
 
+def test_cer_wer_batched_edit_distance(fb):
+    """the batched GPU Levenshtein reproduces the reference's CER / WER exactly (integer DP) on
+    the reference-generated golden pairs, and the oracle on a ragged random batch (empty sequences, length 1,
+    lengths up to 300, many pairs in one launch)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cer_wer_vectors.json")
+    vec = json.load(open(path, encoding="utf-8"))
+    refs, hyps = [v["ref"] for v in vec], [v["hyp"] for v in vec]
+    assert fb.batch_cer(refs, hyps) == [v["cer"] for v in vec]
+    assert fb.batch_wer(refs, hyps) == [v["wer"] for v in vec]
+    assert fb.calculate_cer(refs[3], hyps[3]) == vec[3]["cer"] and fb.calculate_wer(refs[4], hyps[4]) == vec[4]["wer"]
+    rng = np.random.default_rng(4)
+    R = [rng.integers(0, 6, size=int(n)).tolist() for n in rng.integers(0, 300, size=700)]
+    H = [rng.integers(0, 6, size=int(n)).tolist() for n in rng.integers(0, 300, size=700)]
+    R[0], H[0], R[1], H[2] = [], [], [], []
+    from fddm_b200.metrics import _edit_distances
+    got = _edit_distances(R, H)
+    for i in list(range(12)) + rng.integers(0, 700, size=40).tolist():
+        assert got[i] == O.edit_distance(R[i], H[i]), i
+
+
 def test_lfd_shape_assert(fb):
     with pytest.raises(AssertionError):
         fb.lfd_loss(torch.zeros(2, 3, 8, device="cuda"), torch.zeros(2, 3, 16, device="cuda"))

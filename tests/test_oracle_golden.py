@@ -169,3 +169,16 @@ def test_fast_mode_alpha_bar_off_by_one(golden):
     assert O.alpha_bar_at_t_train(0, 20, 200, abar) == 1.0
     with pytest.raises(IndexError):
         O.alpha_bar_at_t_train(20, 20, 200, abar)
+
+
+def test_cer_wer_oracle_matches_reference_golden():
+    """the oracle's Levenshtein CER / WER equal the reference's (models/evaluate.py:94-134) on the
+    committed pairs generated by tests/golden/make_cer_golden.py (CJK + Latin, empty and identical strings)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cer_wer_vectors.json")
+    vec = json.load(open(path, encoding="utf-8"))
+    assert len(vec) >= 60
+    for v in vec:
+        assert O.calculate_cer(v["ref"], v["hyp"]) == v["cer"]
+        assert O.calculate_wer(v["ref"], v["hyp"]) == v["wer"]

@@ -228,6 +228,9 @@ struct JumpParams {
   unsigned int* work;        // self-resetting counters: [0] next row, [1] CTAs done, [2] rows on the fallback list
   int* row_list;             // fallback list (greedy streamed kernel -> bit-faithful kernel), [rows] ints after the counters
   int list_mode;             // 1: rows are row_list[0 .. work[2]) instead of 0 .. rows
+  // streamed kernels: a row is copied in `nchunks` pieces of `chunk_vecs` 16-byte vectors (a multiple of the
+  // consumer thread count, so a thread owns the same vector residues in every chunk) through `nstages` stages
+  int chunk_vecs, nchunks, nstages;
   int B, L, K, rows;
   int flags;
   int abar_index;
@@ -751,6 +754,8 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
   jump_epilogue<NT>(p, tid);
 }
 
+constexpr int kStreamStages = 4;
+
 // ------------------------------------------------------------------------------------------------
 // In-kernel-RNG production kernel ("streamed"): the row is never held in registers.  One shared-memory
 // stage per CTA; the consumers stream over it twice (max, then exp-sum), release it -- the producer's
@@ -765,17 +770,21 @@ jump_rows_ring_kernel(const JumpParams p, const int nstages, const uint32_t stag
 template <typename T, int NT, int CTAS>
 __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const JumpParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
-  __shared__ uint64_t s_full, s_empty;
-  __shared__ RingMeta s_meta;
+  __shared__ uint64_t s_full[kStreamStages], s_empty[kStreamStages];
+  __shared__ RingMeta s_meta[kStreamStages];
   __shared__ float s_red[kRedFloats];
   __shared__ int s_nw[32];
   constexpr int N = Vec16<T>::N, NW = NT / 32;
   constexpr float kLog2e = 1.4426950408889634f;
   constexpr float k2m24 = 1.0f / 16777216.0f;
   const int tid = threadIdx.x;
+  const int nstages = p.nstages, nchunks = p.nchunks;
+  const uint32_t chunk_bytes = static_cast<uint32_t>(p.chunk_vecs) * 16u;
   if (tid == 0) {
-    mbar_init(&s_full, 1);
-    mbar_init(&s_empty, NW);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NW);
+    }
     mbar_fence_init();
     fence_proxy_async();
   }
@@ -785,29 +794,39 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
 
   if (tid >= NT) {
     if (tid == NT) {                       // producer lane
-      for (uint32_t it = 0;; ++it) {
-        if (it > 0) mbar_wait_backoff(&s_empty, (it - 1) & 1);
+      uint32_t it = 0;                     // chunks issued so far: stage = it % nstages
+      for (;;) {
         const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
         if (row >= p.rows) {
-          s_meta.row = -1;
-          mbar_arrive(&s_full);
+          const int s = static_cast<int>(it % nstages);
+          if (it >= static_cast<uint32_t>(nstages)) mbar_wait_backoff(&s_empty[s], (it / nstages - 1) & 1);
+          s_meta[s].row = -1;
+          mbar_arrive(&s_full[s]);
           break;
         }
-        mbar_expect_tx(&s_full, row_bytes);
-        tma_load_1d(dyn_smem, static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes, row_bytes,
-                    &s_full);
-        JumpRowCtx c;
-        jump_load_ctx(p, row, c);
-        RingMeta mt;
-        mt.row = row; mt.w = c.identity ? 0.0f : 1.0f; mt.i0 = c.xt; mt.i1 = 0;
-        mt.f0 = exact ? c.a_c : c.ab;
-        mt.f1 = c.b_c; mt.f2 = c.a_g; mt.f3 = c.b_g;
-        uint2 key, off;
-        philox_key_off(p.philox_state, p.key, p.off, key, off);
-        const uint4 rnd = philox4x32_10(make_uint4(0xffffffffu, static_cast<uint32_t>(row), off.x, off.y ^ kJumpDomain), key);
-        mt.r0 = rnd.x; mt.r1 = rnd.y; mt.r2 = rnd.z;
-        s_meta = mt;
-        mbar_arrive(&s_full);
+        const uint8_t* src = static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int s = static_cast<int>(it % nstages);
+          if (it >= static_cast<uint32_t>(nstages)) mbar_wait_backoff(&s_empty[s], (it / nstages - 1) & 1);
+          const uint32_t off_b = static_cast<uint32_t>(c) * chunk_bytes;
+          const uint32_t bytes = min(chunk_bytes, row_bytes - off_b);
+          mbar_expect_tx(&s_full[s], bytes);
+          tma_load_1d(dyn_smem + static_cast<size_t>(s) * chunk_bytes, src + off_b, bytes, &s_full[s]);
+          if (c == 0) {                    // the row's metadata travels with its first chunk
+            JumpRowCtx cx;
+            jump_load_ctx(p, row, cx);
+            RingMeta mt;
+            mt.row = row; mt.w = cx.identity ? 0.0f : 1.0f; mt.i0 = cx.xt; mt.i1 = 0;
+            mt.f0 = exact ? cx.a_c : cx.ab;
+            mt.f1 = cx.b_c; mt.f2 = cx.a_g; mt.f3 = cx.b_g;
+            uint2 key, off;
+            philox_key_off(p.philox_state, p.key, p.off, key, off);
+            const uint4 rnd = philox4x32_10(make_uint4(0xffffffffu, static_cast<uint32_t>(row), off.x, off.y ^ kJumpDomain), key);
+            mt.r0 = rnd.x; mt.r1 = rnd.y; mt.r2 = rnd.z;
+            s_meta[s] = mt;
+          }
+          mbar_arrive(&s_full[s]);
+        }
       }
     }
     return;
@@ -823,42 +842,57 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
     if (lane == 0) s_nw[warp] = n;         // read only after the first row's block barrier
   }
   RedRing red{s_red, 0};
-  const uint4* sv = reinterpret_cast<const uint4*>(dyn_smem);
   const bool debug_w = (p.flags & FDDM_JUMP_DEBUG_W) != 0;      // test hook: holds the stage like need_p
   const bool need_p = ((p.flags & FDDM_JUMP_WRITE_P) != 0 || p.argmax_p_out != nullptr) && !debug_w;
-  const bool hold = need_p || debug_w;
+  // a one-chunk row stays in its stage for the extra pass that writes p_x0 (or the test hook's weights);
+  // multi-chunk rows hand every chunk back at once and that pass re-reads the row from global memory (L2)
+  const bool hold = (need_p || debug_w) && nchunks == 1;
 
-  for (uint32_t it = 0;; ++it) {
-    mbar_wait(&s_full, it & 1);
-    const RingMeta mt = s_meta;
+  uint32_t it = 0;                         // chunks consumed so far
+  for (;;) {
+    int s0 = static_cast<int>(it % nstages);
+    mbar_wait(&s_full[s0], (it / nstages) & 1);
+    const RingMeta mt = s_meta[s0];
     if (mt.row < 0) break;
     const int xt = mt.i0;
-    // pass 1: thread max (four independent chains)
-    float mx[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
+    const uint4* grow = reinterpret_cast<const uint4*>(static_cast<const T*>(p.logits) + static_cast<size_t>(mt.row) * p.K);
+    const uint4* sv = reinterpret_cast<const uint4*>(dyn_smem + static_cast<size_t>(s0) * chunk_bytes);
+    float m_t = kNegInf, s_t = 0.0f, z_xt = 0.0f;
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const int s = static_cast<int>(it % nstages);
+      if (c > 0) mbar_wait(&s_full[s], (it / nstages) & 1);
+      const uint4* cv = reinterpret_cast<const uint4*>(dyn_smem + static_cast<size_t>(s) * chunk_bytes);
+      const int v0 = c * p.chunk_vecs;
+      const int nv_c = min(p.chunk_vecs, nvec - v0);
+      // pass 1: thread max over the chunk (four independent chains)
+      float mx[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
 #pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      float f[N];
-      Vec16<T>::unpack(sv[vi], f);
+      for (int vi = tid; vi < nv_c; vi += NT) {
+        float f[N];
+        Vec16<T>::unpack(cv[vi], f);
 #pragma unroll
-      for (int e = 0; e < N; ++e) mx[e & 3] = fmaxf(mx[e & 3], f[e]);
-    }
-    const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-    // pass 2: thread sum of exp(z - m_t)
-    const float nm_t = -m_t * kLog2e;
-    float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int e = 0; e < N; ++e) mx[e & 3] = fmaxf(mx[e & 3], f[e]);
+      }
+      const float m_new = fmaxf(m_t, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      // pass 2: thread sum of exp(z - m_new); the running sum is rescaled to the new thread max
+      const float nm_t = -m_new * kLog2e;
+      float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      float f[N];
-      Vec16<T>::unpack(sv[vi], f);
+      for (int vi = tid; vi < nv_c; vi += NT) {
+        float f[N];
+        Vec16<T>::unpack(cv[vi], f);
 #pragma unroll
-      for (int e = 0; e < N; ++e) sx[e & 3] += ex2_approx(fmaf(f[e], kLog2e, nm_t));
+        for (int e = 0; e < N; ++e) sx[e & 3] += ex2_approx(fmaf(f[e], kLog2e, nm_t));
+      }
+      s_t = fmaf(s_t, ex2_approx((m_t - m_new) * kLog2e), (sx[0] + sx[1]) + (sx[2] + sx[3]));
+      m_t = m_new;
+      if (xt >= v0 * N && xt < (v0 + nv_c) * N) z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(cv) + (xt - v0 * N));
+      if (!hold) {                         // hand the stage back: the next copy starts now
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
+      }
     }
-    const float s_t = (sx[0] + sx[1]) + (sx[2] + sx[3]);
-    const float z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(dyn_smem) + xt);
-    if (!hold) {                           // hand the stage back: the next row's copy starts now
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty);
-    }
+    const uint4* psrc = hold ? sv : grow;  // where the optional third pass reads the row
     // warp (max, sum), one block barrier, row (m, S) and the warp masses in every thread
     float m_w = m_t;
 #pragma unroll
@@ -890,7 +924,7 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
 #pragma unroll 2
       for (int vi = tid; vi < nvec; vi += NT) {
         float f[N];
-        Vec16<T>::unpack(sv[vi], f);
+        Vec16<T>::unpack(psrc[vi], f);
 #pragma unroll
         for (int e = 0; e < N; ++e) {
           f[e] = Vec16<T>::round_trip(ex2_approx(fmaf(f[e], kLog2e, nm)) * inv_S);
@@ -898,8 +932,10 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
         }
         if (p_row) stg_stream_v4(reinterpret_cast<uint4*>(p_row) + vi, Vec16<T>::pack(f));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty);
+      if (hold) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s0]);
+      }
       if (p.argmax_p_out) {
         block_argmax<NT>(pm, pm_k, red);
         if (tid == 0) p.argmax_p_out[mt.row] = pm_k;
@@ -910,8 +946,10 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
       if (debug_w) {                       // the target distribution is the one-hot of x_t
         T* w_row = static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K;
         for (int k = tid; k < p.K; k += NT) Vec16<T>::store1(w_row + k, k == xt ? 1.0f : 0.0f);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty);
+        if (hold) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[s0]);
+        }
       }
       continue;
     }
@@ -943,7 +981,7 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
       const float inv_tot = 1.0f / tot;
       for (int vi = tid; vi < nvec; vi += NT) {
         float f[N];
-        Vec16<T>::unpack(sv[vi], f);
+        Vec16<T>::unpack(psrc[vi], f);
 #pragma unroll
         for (int e = 0; e < N; ++e) {
           const float pk = ex2_approx(fmaf(f[e], kLog2e, nm)) * inv_S;
@@ -951,8 +989,10 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
         }
         stg_stream_v4(reinterpret_cast<uint4*>(w_row) + vi, Vec16<T>::pack(f));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty);
+      if (hold) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s0]);
+      }
     }
     const float t1 = tot * ((static_cast<float>(mt.r0 >> 8) + 0.5f) * k2m24);
     int wsel = NW - 1;
@@ -982,7 +1022,6 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
     const int nv_sel = __shfl_sync(0xffffffffu, n_own_vec, lsel);
 
     // the picked lane's entries: its vectors are re-read from global memory, one per lane
-    const uint4* grow = reinterpret_cast<const uint4*>(static_cast<const T*>(p.logits) + static_cast<size_t>(mt.row) * p.K);
     float base = 0.0f;
     int chosen = -1, last_pos = -1;
     for (int j0 = 0; j0 < nv_sel; j0 += 32) {
@@ -1056,16 +1095,20 @@ template <> struct GreedyMargins<__half> { static constexpr float eps_z = 6.0e-3
 template <typename T, int NT, int CTAS>
 __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_greedy_streamed_kernel(const JumpParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
-  __shared__ uint64_t s_full, s_empty;
-  __shared__ RingMeta s_meta;
+  __shared__ uint64_t s_full[kStreamStages], s_empty[kStreamStages];
+  __shared__ RingMeta s_meta[kStreamStages];
   __shared__ float s_red[kRedFloats];
   constexpr int N = Vec16<T>::N, NW = NT / 32;
   constexpr float kLog2e = 1.4426950408889634f;
   constexpr float kEpsZ = GreedyMargins<T>::eps_z, kRel = GreedyMargins<T>::rel;
   const int tid = threadIdx.x;
+  const int nstages = p.nstages, nchunks = p.nchunks;
+  const uint32_t chunk_bytes = static_cast<uint32_t>(p.chunk_vecs) * 16u;
   if (tid == 0) {
-    mbar_init(&s_full, 1);
-    mbar_init(&s_empty, NW);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NW);
+    }
     mbar_fence_init();
     fence_proxy_async();
   }
@@ -1083,30 +1126,40 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_greedy_streamed_kerne
         const float ab = (p.abar_index < 0) ? 1.0f : p.alpha_bar[p.abar_index];
         hopeless = !(ab > 0.0f) || (ab * kEpsZ * 0.5f < kRel * (ab + (1.0f - ab) * p.u));
       }
-      for (uint32_t it = 0;; ++it) {
-        if (it > 0 && !hopeless) mbar_wait_backoff(&s_empty, (it - 1) & 1);
+      uint32_t it = 0;                     // chunks issued so far: stage = it % nstages
+      for (;;) {
         const int row = static_cast<int>(atomicAdd(&p.work[0], 1u));
         if (row >= p.rows) {
-          s_meta.row = -1;
-          mbar_arrive(&s_full);
+          const int s = static_cast<int>(it % nstages);
+          if (it >= static_cast<uint32_t>(nstages)) mbar_wait_backoff(&s_empty[s], (it / nstages - 1) & 1);
+          s_meta[s].row = -1;
+          mbar_arrive(&s_full[s]);
           break;
         }
         if (hopeless) {
           p.row_list[atomicAdd(&p.work[2], 1u)] = row;
           continue;
         }
-        mbar_expect_tx(&s_full, row_bytes);
-        tma_load_1d(dyn_smem, static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes, row_bytes,
-                    &s_full);
-        JumpRowCtx c;
-        jump_load_ctx(p, row, c);
-        RingMeta mt;
-        mt.row = row; mt.w = c.identity ? 0.0f : 1.0f; mt.i0 = c.xt; mt.i1 = 0;
-        mt.f0 = exact ? c.a_c : c.ab;
-        mt.f1 = c.b_c; mt.f2 = c.a_g; mt.f3 = c.b_g;
-        mt.r0 = mt.r1 = mt.r2 = 0u;
-        s_meta = mt;
-        mbar_arrive(&s_full);
+        const uint8_t* src = static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int s = static_cast<int>(it % nstages);
+          if (it >= static_cast<uint32_t>(nstages)) mbar_wait_backoff(&s_empty[s], (it / nstages - 1) & 1);
+          const uint32_t off_b = static_cast<uint32_t>(c) * chunk_bytes;
+          const uint32_t bytes = min(chunk_bytes, row_bytes - off_b);
+          mbar_expect_tx(&s_full[s], bytes);
+          tma_load_1d(dyn_smem + static_cast<size_t>(s) * chunk_bytes, src + off_b, bytes, &s_full[s]);
+          if (c == 0) {
+            JumpRowCtx cx;
+            jump_load_ctx(p, row, cx);
+            RingMeta mt;
+            mt.row = row; mt.w = cx.identity ? 0.0f : 1.0f; mt.i0 = cx.xt; mt.i1 = 0;
+            mt.f0 = exact ? cx.a_c : cx.ab;
+            mt.f1 = cx.b_c; mt.f2 = cx.a_g; mt.f3 = cx.b_g;
+            mt.r0 = mt.r1 = mt.r2 = 0u;
+            s_meta[s] = mt;
+          }
+          mbar_arrive(&s_full[s]);
+        }
       }
     }
     return;
@@ -1115,46 +1168,63 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_greedy_streamed_kerne
   const int lane = tid & 31, warp = tid >> 5;
   const int nvec = p.K / N;
   RedRing red{s_red, 0};
-  const uint4* sv = reinterpret_cast<const uint4*>(dyn_smem);
   const bool need_p = (p.flags & FDDM_JUMP_WRITE_P) != 0 || p.argmax_p_out != nullptr;
+  const bool hold = need_p && nchunks == 1;               // see jump_rows_streamed_kernel
   const float c_thr = ex2_approx(-kEpsZ * kLog2e);        // e_k >= c_thr  <=>  z_k >= m_t - eps_z
 
-  for (uint32_t it = 0;; ++it) {
-    mbar_wait(&s_full, it & 1);
-    const RingMeta mt = s_meta;
+  uint32_t it = 0;                                         // chunks consumed so far
+  for (;;) {
+    const int s0 = static_cast<int>(it % nstages);
+    mbar_wait(&s_full[s0], (it / nstages) & 1);
+    const RingMeta mt = s_meta[s0];
     if (mt.row < 0) break;
     const int xt = mt.i0;
-    // pass 1: thread max
-    float mx[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
-#pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      float f[N];
-      Vec16<T>::unpack(sv[vi], f);
-#pragma unroll
-      for (int e = 0; e < N; ++e) mx[e & 3] = fmaxf(mx[e & 3], f[e]);
-    }
-    const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-    // pass 2: thread sum of exp(z - m_t) and the number of entries within eps_z of the thread max
-    const float nm_t = -m_t * kLog2e;
-    float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const uint4* grow = reinterpret_cast<const uint4*>(static_cast<const T*>(p.logits) + static_cast<size_t>(mt.row) * p.K);
+    const uint4* sv = reinterpret_cast<const uint4*>(dyn_smem + static_cast<size_t>(s0) * chunk_bytes);
+    float m_t = kNegInf, s_t = 0.0f, z_xt = 0.0f;
     int cnt_t = 0;
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const int s = static_cast<int>(it % nstages);
+      if (c > 0) mbar_wait(&s_full[s], (it / nstages) & 1);
+      const uint4* cv = reinterpret_cast<const uint4*>(dyn_smem + static_cast<size_t>(s) * chunk_bytes);
+      const int v0 = c * p.chunk_vecs;
+      const int nv_c = min(p.chunk_vecs, nvec - v0);
+      // pass 1: thread max over the chunk
+      float mx[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
 #pragma unroll 4
-    for (int vi = tid; vi < nvec; vi += NT) {
-      float f[N];
-      Vec16<T>::unpack(sv[vi], f);
+      for (int vi = tid; vi < nv_c; vi += NT) {
+        float f[N];
+        Vec16<T>::unpack(cv[vi], f);
 #pragma unroll
-      for (int e = 0; e < N; ++e) {
-        const float ek = ex2_approx(fmaf(f[e], kLog2e, nm_t));
-        sx[e & 3] += ek;
-        cnt_t += (ek >= c_thr) ? 1 : 0;
+        for (int e = 0; e < N; ++e) mx[e & 3] = fmaxf(mx[e & 3], f[e]);
+      }
+      const float m_new = fmaxf(m_t, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      // entries of earlier chunks counted as contenders stay contenders only if the thread max did not move
+      // beyond eps_z (otherwise they are all below the new threshold); keeping them when in doubt is conservative
+      if (m_new > m_t + kEpsZ) cnt_t = 0;
+      // pass 2: thread sum of exp(z - m_new) and the number of entries within eps_z of the thread max
+      const float nm_t = -m_new * kLog2e;
+      float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+      for (int vi = tid; vi < nv_c; vi += NT) {
+        float f[N];
+        Vec16<T>::unpack(cv[vi], f);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const float ek = ex2_approx(fmaf(f[e], kLog2e, nm_t));
+          sx[e & 3] += ek;
+          cnt_t += (ek >= c_thr) ? 1 : 0;
+        }
+      }
+      s_t = fmaf(s_t, ex2_approx((m_t - m_new) * kLog2e), (sx[0] + sx[1]) + (sx[2] + sx[3]));
+      m_t = m_new;
+      if (xt >= v0 * N && xt < (v0 + nv_c) * N) z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(cv) + (xt - v0 * N));
+      if (!hold) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
       }
     }
-    const float s_t = (sx[0] + sx[1]) + (sx[2] + sx[3]);
-    const float z_xt = Vec16<T>::load1(reinterpret_cast<const T*>(dyn_smem) + xt);
-    if (!need_p) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty);
-    }
+    const uint4* psrc = hold ? sv : grow;
     // warp: max, rescaled sum, contenders (conservative: counted against the thread maxima), owner lane of the max
     float m_w = m_t;
 #pragma unroll
@@ -1194,14 +1264,16 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_greedy_streamed_kerne
 #pragma unroll 2
         for (int vi = tid; vi < nvec; vi += NT) {
           float f[N];
-          Vec16<T>::unpack(sv[vi], f);
+          Vec16<T>::unpack(psrc[vi], f);
 #pragma unroll
           for (int e = 0; e < N; ++e) f[e] = Vec16<T>::round_trip(ex2_approx(fmaf(f[e], kLog2e, nm)) * inv_S);
           stg_stream_v4(reinterpret_cast<uint4*>(p_row) + vi, Vec16<T>::pack(f));
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty);
+      if (hold) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s0]);
+      }
     }
 
     // ---- the decision (every thread evaluates it; the owner warp acts on it) ----
@@ -1239,7 +1311,6 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_greedy_streamed_kerne
     // re-read from global memory (an L2 hit), one vector per lane
     const int tid_top = (wmax << 5) + lmax;
     const int nv_top = (nvec - tid_top + NT - 1) / NT;
-    const uint4* grow = reinterpret_cast<const uint4*>(static_cast<const T*>(p.logits) + static_cast<size_t>(mt.row) * p.K);
     int k_top = -1;
     for (int j0 = 0; j0 < nv_top && k_top < 0; j0 += 32) {
       const int j = j0 + lane;
@@ -1313,63 +1384,50 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
   if (NOISE == 1) aligned = aligned && (noise_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
   const int sms = row_kernel_sms();
   KernelScope ks(NOISE == 0 ? "jump_rows_greedy" : (NOISE == 1 ? "jump_rows_injected_noise" : "jump_rows_philox"), stream);
-  if (NOISE == 2 && aligned && p.temperature == 1.0f && p.work != nullptr && getenv("FDDM_JUMP_CFG") == nullptr) {
-    // streamed kernel: one stage per CTA, resident CTAs limited by shared memory
-    const size_t stage = ((row_bytes + 127) & ~size_t(127)) + 128;
-    int ctas = static_cast<int>((216 * 1024) / (stage + 2048));
-    if (const char* e = getenv("FDDM_JUMP_CTAS")) ctas = std::min(ctas, atoi(e));      // experiment knob
-    if (ctas >= 2) {
-      ctas = std::min(ctas, 6);
-      const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * ctas));
-      const int nvec = p.K / Vec16<T>::N;
-#define FDDM_JUMP_STREAMED(NT_, CTAS_)                                                                      \
+  // Streamed kernels: rows up to 32 KB are one chunk in one stage (6 CTAs/SM at 32 KB); longer rows are copied in
+  // 16 KB chunks through two stages with running (max, sum) per thread -- the same 32 KB of shared memory per CTA,
+  // so six rows are in flight per SM whatever the vocabulary size (and no vocabulary limit on this path).
+  constexpr int kNTs = 128;
+  const int nvec_row = p.K / Vec16<T>::N;
+  JumpParams ps = p;
+  if (row_bytes <= 32 * 1024) { ps.chunk_vecs = (nvec_row + kNTs - 1) / kNTs * kNTs; ps.nchunks = 1; ps.nstages = 1; }
+  else { ps.chunk_vecs = 1024; ps.nchunks = (nvec_row + 1023) / 1024; ps.nstages = 2; }
+  const size_t stream_smem = static_cast<size_t>(ps.chunk_vecs) * 16 * ps.nstages + 128;
+  int stream_ctas = std::min<int>(6, static_cast<int>((216 * 1024) / (stream_smem + 2048)));
+  if (const char* e = getenv("FDDM_JUMP_CTAS")) stream_ctas = std::min(stream_ctas, atoi(e));      // experiment knob
+  const int stream_grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * stream_ctas));
+  if (NOISE == 2 && aligned && p.temperature == 1.0f && p.work != nullptr && getenv("FDDM_JUMP_CFG") == nullptr &&
+      stream_ctas >= 2) {
+#define FDDM_JUMP_STREAMED(CTAS_)                                                                           \
   do {                                                                                                      \
-    auto kfn = jump_rows_streamed_kernel<T, NT_, CTAS_>;                                                    \
-    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage))); \
-    kfn<<<grid, NT_ + 32, stage, stream>>>(p);                                                              \
+    auto kfn = jump_rows_streamed_kernel<T, kNTs, CTAS_>;                                                   \
+    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stream_smem))); \
+    kfn<<<stream_grid, kNTs + 32, stream_smem, stream>>>(ps);                                               \
   } while (0)
-      if (nvec <= 2048) {
-        if (ctas >= 6) FDDM_JUMP_STREAMED(128, 6);
-        else if (ctas >= 4) FDDM_JUMP_STREAMED(128, 4);
-        else FDDM_JUMP_STREAMED(128, 2);
-      } else {
-        if (ctas >= 4) FDDM_JUMP_STREAMED(256, 4);
-        else FDDM_JUMP_STREAMED(256, 2);
-      }
+    if (stream_ctas >= 6) FDDM_JUMP_STREAMED(6);
+    else if (stream_ctas >= 4) FDDM_JUMP_STREAMED(4);
+    else FDDM_JUMP_STREAMED(2);
 #undef FDDM_JUMP_STREAMED
-      FDDM_LAUNCH_OK();
-      return FDDM_OK;
-    }
+    FDDM_LAUNCH_OK();
+    return FDDM_OK;
   }
   if (NOISE == 0 && aligned && p.K <= 32768 && p.work != nullptr && !p.list_mode && p.row_list != nullptr &&
-      getenv("FDDM_JUMP_CFG") == nullptr) {
+      getenv("FDDM_JUMP_CFG") == nullptr && stream_ctas >= 2) {
     // greedy streamed kernel; the rows it does not decide go through the bit-faithful kernel below (list mode)
-    const size_t stage = ((row_bytes + 127) & ~size_t(127)) + 128;
-    int ctas = static_cast<int>((216 * 1024) / (stage + 2048));
-    if (ctas >= 2) {
-      ctas = std::min(ctas, 6);
-      const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * ctas));
-      const int nvec = p.K / Vec16<T>::N;
-#define FDDM_JUMP_GREEDY(NT_, CTAS_)                                                                        \
+#define FDDM_JUMP_GREEDY(CTAS_)                                                                             \
   do {                                                                                                      \
-    auto kfn = jump_rows_greedy_streamed_kernel<T, NT_, CTAS_>;                                             \
-    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage))); \
-    kfn<<<grid, NT_ + 32, stage, stream>>>(p);                                                              \
+    auto kfn = jump_rows_greedy_streamed_kernel<T, kNTs, CTAS_>;                                            \
+    FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stream_smem))); \
+    kfn<<<stream_grid, kNTs + 32, stream_smem, stream>>>(ps);                                               \
   } while (0)
-      if (nvec <= 2048) {
-        if (ctas >= 6) FDDM_JUMP_GREEDY(128, 6);
-        else if (ctas >= 4) FDDM_JUMP_GREEDY(128, 4);
-        else FDDM_JUMP_GREEDY(128, 2);
-      } else {
-        if (ctas >= 4) FDDM_JUMP_GREEDY(256, 4);
-        else FDDM_JUMP_GREEDY(256, 2);
-      }
+    if (stream_ctas >= 6) FDDM_JUMP_GREEDY(6);
+    else if (stream_ctas >= 4) FDDM_JUMP_GREEDY(4);
+    else FDDM_JUMP_GREEDY(2);
 #undef FDDM_JUMP_GREEDY
-      FDDM_LAUNCH_OK();
-      JumpParams q = p;
-      q.list_mode = 1;
-      return launch_jump<T, NOISE>(q, stream);
-    }
+    FDDM_LAUNCH_OK();
+    JumpParams q = p;
+    q.list_mode = 1;
+    return launch_jump<T, NOISE>(q, stream);
   }
   if (aligned && p.K <= 32768 && p.work != nullptr) {
     // (consumer threads, row entries per thread, resident CTAs per SM).  The per-row fixed cost (reductions,
@@ -1511,6 +1569,7 @@ int fddm_jump_step(const void* logits, int dtype, const int64_t* x_t, const floa
   p.work = static_cast<unsigned int*>(workspace);
   p.row_list = workspace ? reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + 128) : nullptr;
   p.list_mode = 0;
+  p.chunk_vecs = 0; p.nchunks = 1; p.nstages = 1;
   p.B = static_cast<int>(B); p.L = static_cast<int>(L); p.K = static_cast<int>(K); p.rows = static_cast<int>(B * L);
   p.flags = flags; p.abar_index = static_cast<int>(abar_index);
   p.temperature = temperature; p.eps = eps;

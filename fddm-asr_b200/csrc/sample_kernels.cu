@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(NT + 32, CTAS) jump_rows_streamed_kernel(const
       T* p_row = (p.flags & FDDM_JUMP_WRITE_P) ? static_cast<T*>(p.p_out) + static_cast<size_t>(mt.row) * p.K : nullptr;
       float pm = -1.0f;
       int pm_k = 0x7fffffff;
-#pragma unroll 2
+#pragma unroll 4
       for (int vi = tid; vi < nvec; vi += NT) {
         float f[N];
         Vec16<T>::unpack(psrc[vi], f);
@@ -1396,8 +1396,13 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
   int stream_ctas = std::min<int>(6, static_cast<int>((216 * 1024) / (stream_smem + 2048)));
   if (const char* e = getenv("FDDM_JUMP_CTAS")) stream_ctas = std::min(stream_ctas, atoi(e));      // experiment knob
   const int stream_grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * stream_ctas));
+  // the pass that writes p_x0 re-reads a multi-chunk row from global memory; measured at V=32000 that is slower
+  // than the register-resident kernel (0.52 vs 0.67 of HBM peak), so the last jump of a chain over long rows
+  // stays on the register-resident kernel while it fits (K <= 32768)
+  const bool wants_p = (p.flags & (FDDM_JUMP_WRITE_P | FDDM_JUMP_DEBUG_W)) != 0 || p.argmax_p_out != nullptr;
+  const bool stream_ok = stream_ctas >= 2 && !(wants_p && ps.nchunks > 1 && p.K <= 32768);
   if (NOISE == 2 && aligned && p.temperature == 1.0f && p.work != nullptr && getenv("FDDM_JUMP_CFG") == nullptr &&
-      stream_ctas >= 2) {
+      stream_ok) {
 #define FDDM_JUMP_STREAMED(CTAS_)                                                                           \
   do {                                                                                                      \
     auto kfn = jump_rows_streamed_kernel<T, kNTs, CTAS_>;                                                   \
@@ -1412,7 +1417,7 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
     return FDDM_OK;
   }
   if (NOISE == 0 && aligned && p.K <= 32768 && p.work != nullptr && !p.list_mode && p.row_list != nullptr &&
-      getenv("FDDM_JUMP_CFG") == nullptr && stream_ctas >= 2) {
+      getenv("FDDM_JUMP_CFG") == nullptr && stream_ok) {
     // greedy streamed kernel; the rows it does not decide go through the bit-faithful kernel below (list mode)
 #define FDDM_JUMP_GREEDY(CTAS_)                                                                             \
   do {                                                                                                      \

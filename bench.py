@@ -395,7 +395,11 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
-    overlap = world > 1 and args.collectives == "overlap"
+    # Running L_fd's forward all-reduces under the KL / jump kernels costs those kernels the reserved SMs (16 of
+    # 148 = 11 % of their time, which grows with the per-GPU batch) and hides a constant ~90 us: it pays below
+    # roughly 40k token rows per GPU (N >= 4 on c5), not above (N = 2: 65k rows).
+    rows_per_gpu = shape_of(args.workload, world)[0] * shape_of(args.workload, world)[1]
+    overlap = world > 1 and (args.collectives == "overlap" or (args.collectives == "auto" and rows_per_gpu <= 40960))
     nccl_ctas = int(os.environ.get("NCCL_MAX_CTAS", "16"))        # 4 / 8 / 16 / 24 / 32 measured at N=8: 16 is best
     if world > 1:
         import torch.distributed as dist
@@ -772,7 +776,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--sampling-mode", default="exact", choices=["exact", "fast"], help="c3 only")
     ap.add_argument("--greedy", action="store_true", help="c3 only: argmax instead of Categorical")
-    ap.add_argument("--collectives", default="overlap", choices=["overlap", "serial"],
+    ap.add_argument("--collectives", default="auto", choices=["auto", "overlap", "serial"],
                     help="N>1: run L_fd's forward all-reduces under the KL / jump kernels (side stream) or in order")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and eager_b200 legs")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")

@@ -16,6 +16,7 @@
 // so the per-element work is one exp, one log (and one reciprocal for the gradient); the <=2 special
 // entries are patched with their exact values.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -297,7 +298,7 @@ __device__ __forceinline__ void kl_epilogue(const KlParams& p, float* red, int* 
 // ------------------------------------------------------------------------------------------------
 // fast path: TMA ring + register-resident rows
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, int EPT, bool BWD>
+template <typename T, int NT, int EPT, bool BWD, bool TIGHT>
 __global__ void __launch_bounds__(NT + 32, (NT <= 256 ? 2 : 1))
 kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -362,9 +363,9 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
   // ===== consumers =====
   const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
   RedRing red{s_red, 0};
-  RegRow<T, NT, EPT> row;
+  RegRow<T, NT, EPT, TIGHT> row;
   row.tid = tid;
-  row.nvec = p.V / RegRow<T, NT, EPT>::N;
+  row.nvec = p.V / RegRow<T, NT, EPT, TIGHT>::N;
   int s = 0;
   uint32_t round = 0;
   for (;;) {
@@ -457,7 +458,9 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
   KernelScope ks(BWD ? "kl_rows_fwdbwd" : "kl_rows_fwd", stream);
   if (aligned && p.V <= 32768) {
     int nt, ept;
+    constexpr int kEpt224 = (sizeof(T) == 4) ? 36 : 40;     // 224 consumers + the producer warp = 8 warps: see below
     if (p.V <= 4096) { nt = 128; ept = 32; }
+    else if (p.V > 7168 && p.V <= 224 * kEpt224 && getenv("FDDM_KL_224") != nullptr) { nt = 224; ept = kEpt224; }
     else if (p.V <= 8192) { nt = 256; ept = 32; }
     else if (p.V <= 16384) { nt = 512; ept = 32; }
     else { nt = 512; ept = 64; }
@@ -465,14 +468,17 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
     if (plan.nstages >= 1) {
       const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
       const uint32_t sb = static_cast<uint32_t>((row_bytes + 127) & ~size_t(127));
+      const int nvec = p.V / Vec16<T>::N, nvec_thr = ept / Vec16<T>::N;
+      const bool tight = nvec > (nvec_thr - 1) * nt && getenv("FDDM_KL_TIGHT") != nullptr;
 #define FDDM_KL_LAUNCH(NT_, EPT_)                                                                           \
   do {                                                                                                      \
-    auto kfn = kl_rows_ring_kernel<T, NT_, EPT_, BWD>;                                                      \
+    auto kfn = tight ? kl_rows_ring_kernel<T, NT_, EPT_, BWD, true> : kl_rows_ring_kernel<T, NT_, EPT_, BWD, false>; \
     FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                       static_cast<int>(plan.smem_bytes)));                                  \
     kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb);                                  \
   } while (0)
       if (nt == 128) FDDM_KL_LAUNCH(128, 32);
+      else if (nt == 224) FDDM_KL_LAUNCH(224, kEpt224);
       else if (nt == 256) FDDM_KL_LAUNCH(256, 32);
       else if (ept == 32) FDDM_KL_LAUNCH(512, 32);
       else FDDM_KL_LAUNCH(512, 64);

@@ -16,7 +16,7 @@
 // so the per-element work is one exp, one log (and one reciprocal for the gradient); the <=2 special
 // entries are patched with their exact values.
 #include <math.h>
-#include <stdlib.h>
+#include <stdio.h>
 
 #include <algorithm>
 
@@ -46,6 +46,7 @@ struct KlParams {
   void* grad;
   int T, B, L, V, rows;
   float inv_bdiv;            // 1 / batch divisor
+  int clamp_t;               // 1: clamp t into 1..T silently; 0: an out-of-range t traps (the reference raises)
 };
 
 constexpr float kEps = 1e-8f;
@@ -80,6 +81,12 @@ __device__ __forceinline__ float token_weight_warp(const KlParams& p, int row, i
 
 __device__ __forceinline__ void load_betas(const KlParams& p, int b, float& beta_t, float& beta_p) {
   long long tt = p.t[b];
+  if ((tt < 1 || tt > p.T) && !p.clamp_t) {
+    // the reference indexes betas[t-1]: IndexError on CPU, device-side assert on CUDA.  Same class of failure
+    // here, without a host synchronisation or an extra launch on the hot path.
+    printf("fddm kl_term: t[%d] = %lld is outside 1..%d\n", b, tt, p.T);
+    __trap();
+  }
   tt = tt < 1 ? 1 : (tt > p.T ? p.T : tt);
   beta_t = p.betas[tt - 1];
   beta_p = (tt == 1) ? 0.0f : p.betas[tt - 2];          // beta_0 := 0  (train.py:214-217)
@@ -298,7 +305,7 @@ __device__ __forceinline__ void kl_epilogue(const KlParams& p, float* red, int* 
 // ------------------------------------------------------------------------------------------------
 // fast path: TMA ring + register-resident rows
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, int EPT, bool BWD, bool TIGHT>
+template <typename T, int NT, int EPT, bool BWD>
 __global__ void __launch_bounds__(NT + 32, (NT <= 256 ? 2 : 1))
 kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -363,9 +370,9 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
   // ===== consumers =====
   const float gscale = (BWD && p.grad_scale) ? __ldg(p.grad_scale) : 1.0f;
   RedRing red{s_red, 0};
-  RegRow<T, NT, EPT, TIGHT> row;
+  RegRow<T, NT, EPT> row;
   row.tid = tid;
-  row.nvec = p.V / RegRow<T, NT, EPT, TIGHT>::N;
+  row.nvec = p.V / RegRow<T, NT, EPT>::N;
   int s = 0;
   uint32_t round = 0;
   for (;;) {
@@ -458,9 +465,7 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
   KernelScope ks(BWD ? "kl_rows_fwdbwd" : "kl_rows_fwd", stream);
   if (aligned && p.V <= 32768) {
     int nt, ept;
-    constexpr int kEpt224 = (sizeof(T) == 4) ? 36 : 40;     // 224 consumers + the producer warp = 8 warps: see below
     if (p.V <= 4096) { nt = 128; ept = 32; }
-    else if (p.V > 7168 && p.V <= 224 * kEpt224 && getenv("FDDM_KL_224") != nullptr) { nt = 224; ept = kEpt224; }
     else if (p.V <= 8192) { nt = 256; ept = 32; }
     else if (p.V <= 16384) { nt = 512; ept = 32; }
     else { nt = 512; ept = 64; }
@@ -468,17 +473,14 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
     if (plan.nstages >= 1) {
       const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
       const uint32_t sb = static_cast<uint32_t>((row_bytes + 127) & ~size_t(127));
-      const int nvec = p.V / Vec16<T>::N, nvec_thr = ept / Vec16<T>::N;
-      const bool tight = nvec > (nvec_thr - 1) * nt && getenv("FDDM_KL_TIGHT") != nullptr;
 #define FDDM_KL_LAUNCH(NT_, EPT_)                                                                           \
   do {                                                                                                      \
-    auto kfn = tight ? kl_rows_ring_kernel<T, NT_, EPT_, BWD, true> : kl_rows_ring_kernel<T, NT_, EPT_, BWD, false>; \
+    auto kfn = kl_rows_ring_kernel<T, NT_, EPT_, BWD>;                                                      \
     FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                       static_cast<int>(plan.smem_bytes)));                                  \
     kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb);                                  \
   } while (0)
       if (nt == 128) FDDM_KL_LAUNCH(128, 32);
-      else if (nt == 224) FDDM_KL_LAUNCH(224, kEpt224);
       else if (nt == 256) FDDM_KL_LAUNCH(256, 32);
       else if (ept == 32) FDDM_KL_LAUNCH(512, 32);
       else FDDM_KL_LAUNCH(512, 64);
@@ -498,7 +500,7 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
 }
 
 int kl_entry(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
-             const void* x_mask, int mask_is_f32, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V, double batch_div,
+             const void* x_mask, int flags, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V, double batch_div,
              const float* grad_scale, void* workspace, float* loss_out, void* grad_logits, bool bwd,
              cudaStream_t stream) {
   FDDM_CHECK_ARG(logits && xt && x0 && t && betas && workspace && loss_out, "kl: null pointer argument");
@@ -514,8 +516,10 @@ int kl_entry(const void* logits, int dtype, const int64_t* xt, const int64_t* x0
   }
   KlParams p;
   p.logits = logits; p.xt = xt; p.x0 = x0; p.t = t; p.betas = betas;
+  const bool mask_is_f32 = (flags & FDDM_KL_MASK_F32) != 0;
   p.mask = mask_is_f32 ? nullptr : static_cast<const uint8_t*>(x_mask);
   p.maskf = mask_is_f32 ? static_cast<const float*>(x_mask) : nullptr;
+  p.clamp_t = (flags & FDDM_KL_CLAMP_T) ? 1 : 0;
   p.grad_scale = grad_scale; p.ws = static_cast<KlWorkspace*>(workspace); p.loss_out = loss_out;
   p.grad = grad_logits;
   p.T = static_cast<int>(T); p.B = static_cast<int>(B); p.L = static_cast<int>(L); p.V = static_cast<int>(V);
@@ -538,20 +542,20 @@ size_t fddm_kl_workspace_bytes(int64_t B, int64_t L) {
 }
 
 int fddm_kl_forward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
-                    const void* x_mask, int mask_is_f32, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
+                    const void* x_mask, int flags, const float* betas, int64_t T, int64_t B, int64_t L, int64_t V,
                     double batch_div, void* workspace, float* loss_out, fddm_stream_t stream) {
   FDDM_API_RANGE();
-  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, mask_is_f32, betas, T, B, L, V, batch_div, nullptr, workspace,
+  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, flags, betas, T, B, L, V, batch_div, nullptr, workspace,
                         loss_out, nullptr, false, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fddm_kl_forward_backward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0, const int64_t* t,
-                             const void* x_mask, int mask_is_f32, const float* betas, int64_t T, int64_t B, int64_t L,
+                             const void* x_mask, int flags, const float* betas, int64_t T, int64_t B, int64_t L,
                              int64_t V,
                              double batch_div, const float* grad_scale, void* workspace, float* loss_out,
                              void* grad_logits, fddm_stream_t stream) {
   FDDM_API_RANGE();
-  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, mask_is_f32, betas, T, B, L, V, batch_div, grad_scale,
+  return fddm::kl_entry(logits, dtype, xt, x0, t, x_mask, flags, betas, T, B, L, V, batch_div, grad_scale,
                         workspace, loss_out, grad_logits, true, reinterpret_cast<cudaStream_t>(stream));
 }
 

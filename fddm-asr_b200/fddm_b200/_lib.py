@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("FDDM_B200_LIB") or os.path.join(os.path.dirname(_HERE
 F32, BF16, F16 = 0, 1, 2
 JUMP_EXACT, JUMP_SAMPLE, JUMP_WRITE_P, JUMP_DEBUG_W = 0x1, 0x2, 0x4, 0x8
 LFD_PLANES_VALID = 0x2
+KL_MASK_F32, KL_CLAMP_T = 0x1, 0x2
 MAX_VOCAB = 49152
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}

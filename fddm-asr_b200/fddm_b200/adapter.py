@@ -34,14 +34,15 @@ class _KLTermFn(torch.autograd.Function):
     rescales it in place only if the actual upstream gradient differs."""
 
     @staticmethod
-    def forward(ctx, logits, xt, x0, t, mask, betas, T, batch_div, grad_scale, group):
+    def forward(ctx, logits, xt, x0, t, mask, betas, T, batch_div, grad_scale, group, clamp_t):
         B, Lq, V = logits.shape
         dev = logits.device
         ws = L.zeroed_workspace(dev, "kl", int(L.lib.fddm_kl_workspace_bytes(B, Lq)))
         loss = torch.empty((), dtype=torch.float32, device=dev)
         need_grad = ctx.needs_input_grad[0]
         dt = L.dtype_code(logits)
-        mask_f32 = 1 if (mask is not None and mask.dtype == torch.float32) else 0
+        mask_f32 = (L.KL_MASK_F32 if (mask is not None and mask.dtype == torch.float32) else 0) | \
+                   (L.KL_CLAMP_T if clamp_t else 0)
         if need_grad:
             grad = torch.empty_like(logits)
             L.check(L.lib.fddm_kl_forward_backward(logits.data_ptr(), dt, xt.data_ptr(), x0.data_ptr(), t.data_ptr(),
@@ -69,7 +70,7 @@ class _KLTermFn(torch.autograd.Function):
         L.check(L.lib.fddm_scale_inplace(grad.data_ptr(), L.dtype_code(grad), grad.numel(), g.data_ptr(),
                                          scale.data_ptr() if ctx.has_scale else None, L.stream_ptr(grad.device)),
                 "scale_inplace")
-        return grad, None, None, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None, None, None
 
 
 class SchedulerAdapter:
@@ -87,7 +88,7 @@ class SchedulerAdapter:
         self._grad_scale = grad_scale
         self._group = group
         self._defer = bool(defer_reduce)
-        self._validate_t = bool(validate_t)     # device-side assert 1 <= t <= T (no host sync); the kernels clamp
+        self._validate_t = bool(validate_t)     # in-kernel trap on t outside 1..T (False: clamp silently)
 
     # -- train.py:180-188 ------------------------------------------------------------------------
     def sample_q(self, x0: torch.Tensor, t: torch.Tensor, *, exp_noise=None, generator=None,
@@ -114,16 +115,14 @@ class SchedulerAdapter:
         if betas.dtype != torch.float32 or not betas.is_contiguous():
             betas = betas.float().contiguous()
         mask = _as_mask(None if x_mask is None else x_mask.to(dev), B, Lq)
-        if self._validate_t and not torch.cuda.is_current_stream_capturing():
-            # the reference indexes betas[t-1]: out-of-range t is an IndexError on CPU and a device-side assert
-            # on CUDA.  Same here, without a host sync: an asynchronous device-side assert.
-            torch._assert_async(((t >= 1) & (t <= int(betas.numel()))).all())
         world = 1 if self._group is None else torch.distributed.get_world_size(self._group)
         gs = self._grad_scale() if callable(self._grad_scale) else self._grad_scale
         if gs is not None:
             gs = gs.detach().to(device=dev, dtype=torch.float32).reshape(())
+        # validate_t: the kernel itself traps on a t outside 1..T (the reference raises: IndexError on CPU, device-side
+        # assert on CUDA) -- no host synchronisation and no extra launch; validate_t=False clamps silently instead
         return _KLTermFn.apply(logits, xt, x0, t, mask, betas, int(betas.numel()), B * world, gs,
-                               None if self._defer else self._group)
+                               None if self._defer else self._group, not self._validate_t)
 
     # -- train.py:257-273 ------------------------------------------------------------------------
     def w_t(self, t: torch.Tensor) -> torch.Tensor:

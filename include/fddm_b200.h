@@ -121,9 +121,12 @@ int fddm_q_posterior_multi_dense(const float* xt_prob, const float* x0hat_prob, 
  * variant additionally writes d loss / d logits in the same pass (logits are read exactly once).
  *
  *   logits      [B,L,V] dtype `dtype`           xt, x0  int64 [B,L]        t  int64 [B]
- *   x_mask      NULL (plain mean over L), or [B,L] uint8/bool (mask_is_f32 = 0: non-zero = valid), or [B,L]
- *               fp32 WEIGHTS (mask_is_f32 = 1): the reference multiplies by x_mask.float() (train:250), so a
- *               non-boolean mask acts as per-token weights sum_l w KL / (sum_l w + eps)
+ *   x_mask      NULL (plain mean over L), or [B,L] uint8/bool (non-zero = valid), or -- flags & FDDM_KL_MASK_F32 --
+ *               [B,L] fp32 WEIGHTS: the reference multiplies by x_mask.float() (train:250), so a non-boolean mask
+ *               acts as per-token weights sum_l w KL / (sum_l w + eps)
+ *   flags       FDDM_KL_MASK_F32 | FDDM_KL_CLAMP_T.  Without CLAMP_T a t outside 1..T makes the kernel print the
+ *               offending value and trap (the reference raises: IndexError on CPU, device-side assert on CUDA);
+ *               with it t is clamped silently
  *   batch_div   the divisor of the final batch mean (B for one process; the GLOBAL batch when the
  *               batch is sharded over ranks -- then *loss_out is this rank's partial sum / batch_div
  *               and an all-reduce SUM completes it)
@@ -131,13 +134,15 @@ int fddm_q_posterior_multi_dense(const float* xt_prob, const float* x0hat_prob, 
  *   loss_out    fp32 scalar
  *   grad_scale  fp32 device scalar multiplied into the gradient (upstream dL/dloss), NULL = 1
  *   grad_logits [B,L,V] dtype `dtype` (the reference's grad has the logits dtype) */
+#define FDDM_KL_MASK_F32 0x1
+#define FDDM_KL_CLAMP_T  0x2
 size_t fddm_kl_workspace_bytes(int64_t B, int64_t L);
 int fddm_kl_forward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0,
-                    const int64_t* t, const void* x_mask, int mask_is_f32, const float* betas, int64_t T,
+                    const int64_t* t, const void* x_mask, int flags, const float* betas, int64_t T,
                     int64_t B, int64_t L, int64_t V, double batch_div, void* workspace,
                     float* loss_out, fddm_stream_t stream);
 int fddm_kl_forward_backward(const void* logits, int dtype, const int64_t* xt, const int64_t* x0,
-                             const int64_t* t, const void* x_mask, int mask_is_f32, const float* betas, int64_t T,
+                             const int64_t* t, const void* x_mask, int flags, const float* betas, int64_t T,
                              int64_t B, int64_t L, int64_t V, double batch_div,
                              const float* grad_scale, void* workspace, float* loss_out,
                              void* grad_logits, fddm_stream_t stream);

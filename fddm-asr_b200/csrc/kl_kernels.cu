@@ -60,9 +60,12 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 
 // weight of one token in the loss: mask/(sum_l mask + eps)/Bdiv, or 1/L/Bdiv without a mask
 // (train.py:249-255).  Evaluated by one full warp.
+// MASKF selects the fp32-weight variant at compile time: with it in the common (bool / no mask) instantiation the
+// main kernel measured 9 % slower (199 vs 183 us at the c5 shard) although the code is never executed there.
+template <bool MASKF>
 __device__ __forceinline__ float token_weight_warp(const KlParams& p, int row, int lane) {
   const int b = row / p.L;
-  if (p.maskf != nullptr) {
+  if (MASKF) {
     const float* mrow = p.maskf + static_cast<size_t>(b) * p.L;
     float c = 0.0f;
     for (int l = lane; l < p.L; l += 32) c += mrow[l];
@@ -244,7 +247,7 @@ __device__ __forceinline__ float kl_row_math(Row& row, const int V, const int xt
 }
 
 // last CTA: masked per-sample means and the batch mean, in a fixed order (deterministic)
-template <int NT>
+template <int NT, bool MASKF>
 __device__ __forceinline__ void kl_finalize(const KlParams& p, float* red, int tid) {
   constexpr int NW = NT / 32;
   const int warp = tid >> 5, lane = tid & 31;
@@ -256,7 +259,7 @@ __device__ __forceinline__ void kl_finalize(const KlParams& p, float* red, int t
     for (int l = lane; l < p.L; l += 32) {
       const size_t i = static_cast<size_t>(b) * p.L + l;
       const float k = __ldcg(&p.ws->kl_tok[i]);
-      if (p.maskf) {
+      if (MASKF) {
         const float wgt = p.maskf[i];
         cf += wgt;
         s += (wgt != 0.0f) ? k * wgt : 0.0f;
@@ -271,9 +274,11 @@ __device__ __forceinline__ void kl_finalize(const KlParams& p, float* red, int t
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     c = warp_sum_int(c);
+    if (MASKF) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cf += __shfl_xor_sync(0xffffffffu, cf, o);
-    acc += p.maskf ? s / (cf + kEps) : (p.mask ? s / (static_cast<float>(c) + kEps) : s / static_cast<float>(p.L));
+      for (int o = 16; o > 0; o >>= 1) cf += __shfl_xor_sync(0xffffffffu, cf, o);
+    }
+    acc += MASKF ? s / (cf + kEps) : (p.mask ? s / (static_cast<float>(c) + kEps) : s / static_cast<float>(p.L));
   }
   if (lane == 0) red[warp] = acc;
   consumer_sync<NT>();
@@ -287,7 +292,7 @@ __device__ __forceinline__ void kl_finalize(const KlParams& p, float* red, int t
   }
 }
 
-template <int NT>
+template <int NT, bool MASKF>
 __device__ __forceinline__ void kl_epilogue(const KlParams& p, float* red, int* s_flag, int tid) {
   consumer_sync<NT>();
   if (tid == 0) {
@@ -298,14 +303,14 @@ __device__ __forceinline__ void kl_epilogue(const KlParams& p, float* red, int* 
   consumer_sync<NT>();
   if (*s_flag) {
     __threadfence();
-    kl_finalize<NT>(p, red, tid);
+    kl_finalize<NT, MASKF>(p, red, tid);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // fast path: TMA ring + register-resident rows
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, int EPT, bool BWD>
+template <typename T, int NT, int EPT, bool BWD, bool MASKF>
 __global__ void __launch_bounds__(NT + 32, (NT <= 256 ? 2 : 1))
 kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -343,7 +348,7 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
         }
         break;
       }
-      const float w = token_weight_warp(p, row, lane);
+      const float w = token_weight_warp<MASKF>(p, row, lane);
       if (lane == 0) {
         RingMeta mt;
         mt.row = row;
@@ -396,13 +401,13 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
     }
     if (++s == nstages) { s = 0; ++round; }
   }
-  kl_epilogue<NT>(p, s_red, &s_flag, tid);
+  kl_epilogue<NT, MASKF>(p, s_red, &s_flag, tid);
 }
 
 // ------------------------------------------------------------------------------------------------
 // generic path: any V <= FDDM_MAX_VOCAB, any alignment; the row is an fp32 copy in shared memory
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, bool BWD>
+template <typename T, int NT, bool BWD, bool MASKF>
 __global__ void __launch_bounds__(NT, 1) kl_rows_generic_kernel(const KlParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ float s_red[kRedFloats];
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(NT, 1) kl_rows_generic_kernel(const KlParams p
   RedRing red{s_red, 0};
   SmemRow<T, NT> row;
   for (int r = blockIdx.x; r < p.rows; r += gridDim.x) {
-    const float w = token_weight_warp(p, r, tid & 31);
+    const float w = token_weight_warp<MASKF>(p, r, tid & 31);
     T* grad_row = BWD ? static_cast<T*>(p.grad) + static_cast<size_t>(r) * p.V : nullptr;
     if (w == 0.0f) {
       if (BWD) for (int k = tid; k < p.V; k += NT) Vec16<T>::store1(grad_row + k, 0.0f);
@@ -431,7 +436,7 @@ __global__ void __launch_bounds__(NT, 1) kl_rows_generic_kernel(const KlParams p
     if (tid == 0) p.ws->kl_tok[r] = kl;
     consumer_sync<NT>();      // row buffer is reused by the next iteration
   }
-  kl_epilogue<NT>(p, s_red, &s_flag, tid);
+  kl_epilogue<NT, MASKF>(p, s_red, &s_flag, tid);
 }
 
 // x *= num/den, all CTAs leave immediately when the ratio is exactly 1
@@ -475,7 +480,7 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
       const uint32_t sb = static_cast<uint32_t>((row_bytes + 127) & ~size_t(127));
 #define FDDM_KL_LAUNCH(NT_, EPT_)                                                                           \
   do {                                                                                                      \
-    auto kfn = kl_rows_ring_kernel<T, NT_, EPT_, BWD>;                                                      \
+    auto kfn = p.maskf ? kl_rows_ring_kernel<T, NT_, EPT_, BWD, true> : kl_rows_ring_kernel<T, NT_, EPT_, BWD, false>; \
     FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                       static_cast<int>(plan.smem_bytes)));                                  \
     kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb);                                  \
@@ -491,7 +496,7 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
   }
   // generic path
   const size_t smem = static_cast<size_t>(p.V) * sizeof(float) + 128;
-  auto kfn = kl_rows_generic_kernel<T, 256, BWD>;
+  auto kfn = p.maskf ? kl_rows_generic_kernel<T, 256, BWD, true> : kl_rows_generic_kernel<T, 256, BWD, false>;
   FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * 4));
   kfn<<<grid, 256, smem, stream>>>(p);

@@ -1383,7 +1383,11 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
                  (!(p.flags & (FDDM_JUMP_WRITE_P | FDDM_JUMP_DEBUG_W)) || reinterpret_cast<uintptr_t>(p.p_out) % 16 == 0);
   if (NOISE == 1) aligned = aligned && (noise_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(p.noise) % 16 == 0);
   const int sms = row_kernel_sms();
-  KernelScope ks(NOISE == 0 ? "jump_rows_greedy" : (NOISE == 1 ? "jump_rows_injected_noise" : "jump_rows_philox"), stream);
+  // (the greedy scope spans the streamed kernel AND the bit-faithful pass over its fallback list, which also
+  //  records itself under its own name)
+  KernelScope ks(p.list_mode ? "jump_rows_bitfaithful_list"
+                             : (NOISE == 0 ? "jump_rows_greedy" : (NOISE == 1 ? "jump_rows_injected_noise" : "jump_rows_philox")),
+                 stream);
   // Streamed kernels: rows up to 32 KB are one chunk in one stage (6 CTAs/SM at 32 KB); longer rows are copied in
   // 16 KB chunks through two stages with running (max, sum) per thread -- the same 32 KB of shared memory per CTA,
   // so six rows are in flight per SM whatever the vocabulary size (and no vocabulary limit on this path).

@@ -17,6 +17,7 @@
 // entries are patched with their exact values.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -47,6 +48,7 @@ struct KlParams {
   int T, B, L, V, rows;
   float inv_bdiv;            // 1 / batch divisor
   int clamp_t;               // 1: clamp t into 1..T silently; 0: an out-of-range t traps (the reference raises)
+  int batch;                 // rows a producer warp claims at once (<= 32, one lane per row's metadata)
 };
 
 constexpr float kEps = 1e-8f;
@@ -333,41 +335,81 @@ kl_rows_ring_kernel(const KlParams p, const int nstages, const uint32_t stage_by
 
   if (tid >= NT) {
     // ===== producer warp =====
+    // A row's metadata costs a chain of dependent global loads (row claim -> mask row -> ids, t -> betas), about
+    // 2 us, and a single lane doing that row after row bounded the whole kernel (the forward-only kernel took
+    // as long per row as forward+backward: the consumers were starved).  So the warp claims `batch` consecutive
+    // rows at once and every lane prepares ONE row's metadata in parallel; the copies are then issued in row
+    // order as stages free up, with nothing but the stage hand-shake on that path.
     const int lane = tid - NT;
+    const int batch = p.batch;
     int s = 0;
     uint32_t round = 0;
     for (;;) {
-      if (round > 0) mbar_wait_backoff(&ring.empty[s], (round - 1) & 1);
-      int row = 0;
-      if (lane == 0) row = static_cast<int>(atomicAdd(&p.ws->next_row, 1u));
-      row = __shfl_sync(0xffffffffu, row, 0);
-      if (row >= p.rows) {
+      int base = 0;
+      if (lane == 0) base = static_cast<int>(atomicAdd(&p.ws->next_row, static_cast<unsigned int>(batch)));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= p.rows) {
+        if (round > 0) mbar_wait_backoff(&ring.empty[s], (round - 1) & 1);
         if (lane == 0) {
           ring.meta[s].row = -1;
           mbar_arrive(&ring.full[s]);
         }
         break;
       }
-      const float w = token_weight_warp<MASKF>(p, row, lane);
-      if (lane == 0) {
-        RingMeta mt;
-        mt.row = row;
-        mt.w = w;
-        mt.i0 = static_cast<int>(p.xt[row]);
-        mt.i1 = static_cast<int>(p.x0[row]);
-        load_betas(p, row / p.L, mt.f0, mt.f1);
-        mt.f2 = 0.0f; mt.f3 = 0.0f;
-        mt.r0 = mt.r1 = mt.r2 = 0u;
-        ring.meta[s] = mt;
-        if (w != 0.0f) {
-          mbar_arrive_expect_tx(&ring.full[s], row_bytes);
-          tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
-                      row_bytes, &ring.full[s]);
-        } else {
-          mbar_arrive(&ring.full[s]);
+      const int nb = min(batch, p.rows - base);
+      const int row = base + lane;                       // this lane's row (lanes >= nb idle)
+      const bool mine = lane < nb;
+      const int b = (mine ? row : base) / p.L;
+      // token weights: one warp-cooperative count per distinct sample of the batch
+      float w = 0.0f;
+      if (!MASKF && p.mask == nullptr) {
+        w = (1.0f / static_cast<float>(p.L)) * p.inv_bdiv;
+      } else {
+        const int b_first = base / p.L, b_last = (base + nb - 1) / p.L;
+        for (int bb = b_first; bb <= b_last; ++bb) {
+          float inv;
+          if (MASKF) {
+            const float* mrow = p.maskf + static_cast<size_t>(bb) * p.L;
+            float c = 0.0f;
+            for (int l = lane; l < p.L; l += 32) c += mrow[l];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            inv = 1.0f / (c + kEps);
+          } else {
+            const uint8_t* mrow = p.mask + static_cast<size_t>(bb) * p.L;
+            int c = 0;
+            for (int l = lane; l < p.L; l += 32) c += (mrow[l] != 0);
+            inv = 1.0f / (static_cast<float>(warp_sum_int(c)) + kEps);
+          }
+          if (mine && b == bb) w = (MASKF ? p.maskf[row] : (p.mask[row] != 0 ? 1.0f : 0.0f)) * inv * p.inv_bdiv;
         }
       }
-      if (++s == nstages) { s = 0; ++round; }
+      RingMeta mt;
+      mt.row = row;
+      mt.w = w;
+      mt.i0 = mt.i1 = 0;
+      mt.f0 = mt.f1 = mt.f2 = mt.f3 = 0.0f;
+      mt.r0 = mt.r1 = mt.r2 = 0u;
+      if (mine) {
+        mt.i0 = static_cast<int>(p.xt[row]);
+        mt.i1 = static_cast<int>(p.x0[row]);
+        load_betas(p, b, mt.f0, mt.f1);
+      }
+      for (int k = 0; k < nb; ++k) {
+        if (round > 0) mbar_wait_backoff(&ring.empty[s], (round - 1) & 1);
+        if (lane == k) {
+          ring.meta[s] = mt;
+          if (w != 0.0f) {
+            mbar_arrive_expect_tx(&ring.full[s], row_bytes);
+            tma_load_1d(ring.stage(s), static_cast<const uint8_t*>(p.logits) + static_cast<size_t>(row) * row_bytes,
+                        row_bytes, &ring.full[s]);
+          } else {
+            mbar_arrive(&ring.full[s]);
+          }
+        }
+        __syncwarp();
+        if (++s == nstages) { s = 0; ++round; }
+      }
     }
     return;
   }
@@ -478,12 +520,17 @@ int launch_kl(const KlParams& p, cudaStream_t stream) {
     if (plan.nstages >= 1) {
       const int grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * plan.ctas_per_sm));
       const uint32_t sb = static_cast<uint32_t>((row_bytes + 127) & ~size_t(127));
+      // rows per claim: at least ~8 claims per CTA for load balance, at most one row per producer lane
+      KlParams pb = p;
+      pb.batch = 1;
+      while (pb.batch < 32 && static_cast<int64_t>(pb.batch) * 2 * grid * 8 <= p.rows) pb.batch *= 2;
+      if (const char* e = getenv("FDDM_KL_BATCH")) pb.batch = std::max(1, std::min(32, atoi(e)));   // experiment knob
 #define FDDM_KL_LAUNCH(NT_, EPT_)                                                                           \
   do {                                                                                                      \
     auto kfn = p.maskf ? kl_rows_ring_kernel<T, NT_, EPT_, BWD, true> : kl_rows_ring_kernel<T, NT_, EPT_, BWD, false>; \
     FDDM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                       static_cast<int>(plan.smem_bytes)));                                  \
-    kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb);                                  \
+    kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(pb, plan.nstages, sb);                                 \
   } while (0)
       if (nt == 128) FDDM_KL_LAUNCH(128, 32);
       else if (nt == 256) FDDM_KL_LAUNCH(256, 32);
@@ -525,6 +572,7 @@ int kl_entry(const void* logits, int dtype, const int64_t* xt, const int64_t* x0
   p.mask = mask_is_f32 ? nullptr : static_cast<const uint8_t*>(x_mask);
   p.maskf = mask_is_f32 ? static_cast<const float*>(x_mask) : nullptr;
   p.clamp_t = (flags & FDDM_KL_CLAMP_T) ? 1 : 0;
+  p.batch = 1;
   p.grad_scale = grad_scale; p.ws = static_cast<KlWorkspace*>(workspace); p.loss_out = loss_out;
   p.grad = grad_logits;
   p.T = static_cast<int>(T); p.B = static_cast<int>(B); p.L = static_cast<int>(L); p.V = static_cast<int>(V);

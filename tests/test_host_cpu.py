@@ -100,6 +100,32 @@ def test_host_only_entry_points():
     # argument validation happens before any CUDA call: null pointers -> EINVAL + message
     rc = lib.fddm_q_sample_dense(None, None, None, 10, 1, 1, 8, 1e-8, None, None)
     assert rc == -1 and b"null" in lib.fddm_last_error()
+    # L_fd row order: B < 32 keeps the natural order (one partial per (t, d)); B >= 32 is tb-major with the batch
+    # padded to a multiple of 32 and one partial per 32 batch rows
+    assert [lib.fddm_lfd_bn_parts(B, 7, 64) for B in (1, 4, 31, 32, 33, 64, 130, 512)] == [1, 1, 1, 1, 2, 2, 5, 16]
+    assert lib.fddm_lfd_workspace_bytes(33, 128, 768) > lib.fddm_lfd_workspace_bytes(32, 128, 768)   # padded planes
+    assert lib.fddm_jump_workspace_bytes(8, 64) == 128 + 8 * 64 * 4 and lib.fddm_jump_workspace_bytes(0, 64) == 0
+    assert lib.fddm_edit_distance_workspace_bytes(10, 99) == 10 * 100 * 4
+    assert lib.fddm_set_sm_reserve(16) == 0 and lib.fddm_set_sm_reserve(0) == 0
+    assert lib.fddm_set_sm_reserve(-1) == -1 and b"set_sm_reserve" in lib.fddm_last_error()
+    rc = lib.fddm_edit_distance(None, None, None, None, 1, 4, None, None, None)
+    assert rc == -1 and b"null" in lib.fddm_last_error()
+    # the measurement aid works without a device: nothing recorded -> empty report
+    fddm_b200._lib.profile_enable(True)
+    assert fddm_b200._lib.profile_read() == {}
+    fddm_b200._lib.profile_enable(False)
+
+
+def test_metrics_host_logic_rejects_cpu_only_runs():
+    """calculate_cer / calculate_wer mirror models/evaluate.py:94-134; like every op of the package they have no
+    CPU fallback (the oracle restatement lives in oracle/fddm_oracle.py and is pinned by test_oracle_golden.py)."""
+    import fddm_b200 as fb
+    assert fb.batch_cer([], []) == [] and fb.batch_wer([], []) == []
+    with pytest.raises(ValueError):
+        fb.batch_cer(["a"], ["a", "b"])
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError):
+            fb.calculate_cer("abc", "abd")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -314,10 +314,7 @@ int umma_bwd_gemm(const PackedOperand& Z, const PackedOperand& G, const PackedOp
   p.D = static_cast<int>(D);
   p.tiles_n = static_cast<int>((D + kBwdBN - 1) / kBwdBN);
   p.num_kb = static_cast<int>((D + kBK - 1) / kBK);
-  static const int cl = [] {                                          // FDDM_BWD_CLUSTER=1 falls back to single CTAs
-    const char* e = getenv("FDDM_BWD_CLUSTER");
-    return (e != nullptr && e[0] == '1') ? 1 : 2;
-  }();
+  constexpr int cl = 2;                                              // CTA pair sharing the multicast G tile
   int64_t tiles_m = (rows.rows_packed + kBM - 1) / kBM;              // R_pad is a multiple of 256 >= rows_packed
   tiles_m = (tiles_m + cl - 1) / cl * cl;                            // whole clusters (the extra tile is all zeros)
   const int64_t total = tiles_m / cl * p.tiles_n;                    // work items per cluster
@@ -340,13 +337,8 @@ int umma_bwd_gemm(const PackedOperand& Z, const PackedOperand& G, const PackedOp
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cl == 2) {
-    FDDM_CUDA_OK(cudaFuncSetAttribute(umma_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    FDDM_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_bwd_kernel<2>, p));
-  } else {
-    FDDM_CUDA_OK(cudaFuncSetAttribute(umma_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    FDDM_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_bwd_kernel<1>, p));
-  }
+  FDDM_CUDA_OK(cudaFuncSetAttribute(umma_bwd_kernel<cl>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  FDDM_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_bwd_kernel<cl>, p));
   FDDM_LAUNCH_OK();
   return FDDM_OK;
 }

@@ -1398,15 +1398,13 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
   else { ps.chunk_vecs = 1024; ps.nchunks = (nvec_row + 1023) / 1024; ps.nstages = 2; }
   const size_t stream_smem = static_cast<size_t>(ps.chunk_vecs) * 16 * ps.nstages + 128;
   int stream_ctas = std::min<int>(6, static_cast<int>((216 * 1024) / (stream_smem + 2048)));
-  if (const char* e = getenv("FDDM_JUMP_CTAS")) stream_ctas = std::min(stream_ctas, atoi(e));      // experiment knob
   const int stream_grid = static_cast<int>(std::min<int64_t>(p.rows, static_cast<int64_t>(sms) * stream_ctas));
   // the pass that writes p_x0 re-reads a multi-chunk row from global memory; measured at V=32000 that is slower
   // than the register-resident kernel (0.52 vs 0.67 of HBM peak), so the last jump of a chain over long rows
   // stays on the register-resident kernel while it fits (K <= 32768)
   const bool wants_p = (p.flags & (FDDM_JUMP_WRITE_P | FDDM_JUMP_DEBUG_W)) != 0 || p.argmax_p_out != nullptr;
   const bool stream_ok = stream_ctas >= 2 && !(wants_p && ps.nchunks > 1 && p.K <= 32768);
-  if (NOISE == 2 && aligned && p.temperature == 1.0f && p.work != nullptr && getenv("FDDM_JUMP_CFG") == nullptr &&
-      stream_ok) {
+  if (NOISE == 2 && aligned && p.temperature == 1.0f && p.work != nullptr && stream_ok) {
 #define FDDM_JUMP_STREAMED(CTAS_)                                                                           \
   do {                                                                                                      \
     auto kfn = jump_rows_streamed_kernel<T, kNTs, CTAS_>;                                                   \
@@ -1421,7 +1419,7 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
     return FDDM_OK;
   }
   if (NOISE == 0 && aligned && p.K <= 32768 && p.work != nullptr && !p.list_mode && p.row_list != nullptr &&
-      getenv("FDDM_JUMP_CFG") == nullptr && stream_ok) {
+      stream_ok) {
     // greedy streamed kernel; the rows it does not decide go through the bit-faithful kernel below (list mode)
 #define FDDM_JUMP_GREEDY(CTAS_)                                                                             \
   do {                                                                                                      \
@@ -1446,19 +1444,8 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
     else if (p.K <= 8192) { nt = (NOISE == 2) ? 128 : 256; ept = (NOISE == 2) ? 64 : 32; ctas = (NOISE == 2) ? 3 : 2; }
     else if (p.K <= 16384) { nt = 512; ept = 32; ctas = 1; }
     else { nt = 512; ept = 64; ctas = 1; }
-    int force_stages = 0;
-    if (const char* e = getenv("FDDM_JUMP_CFG")) {               // experiment knob: "NTxEPTxCTAS[xSTAGES]"
-      int a = 0, b = 0, c3 = 0, d = 0;
-      if (sscanf(e, "%dx%dx%dx%d", &a, &b, &c3, &d) >= 3 && NOISE == 2 && p.K <= 8192 && p.K > 4096) {
-        nt = a; ept = b; ctas = c3; force_stages = d;
-      }
-    }
     const size_t row_pad = (row_bytes + 127) & ~size_t(127);
-    RingPlan plan = plan_ring(row_pad + noise_bytes, nt, ctas, force_stages == 1 ? 1 : 2);
-    if (force_stages > 0 && force_stages <= plan.nstages) {
-      plan.nstages = force_stages;
-      plan.smem_bytes = ((row_pad + noise_bytes + 127) & ~size_t(127)) * force_stages + 128;
-    }
+    const RingPlan plan = plan_ring(row_pad + noise_bytes, nt, ctas, 2);
     if (plan.nstages >= 1) {
       // (list mode: the number of listed rows is only known on the device -- it can be all of them, e.g. fast
       //  mode at a noisy step where the uniform mix swamps every difference -- so the grid stays full; CTAs
@@ -1473,9 +1460,7 @@ int launch_jump(const JumpParams& p, cudaStream_t stream) {
     kfn<<<grid, NT_ + 32, plan.smem_bytes, stream>>>(p, plan.nstages, sb, static_cast<uint32_t>(row_pad));  \
   } while (0)
       if (NOISE == 2 && nt == 128 && ept == 32) FDDM_JUMP_LAUNCH(128, 32, 4);
-      else if (NOISE == 2 && nt == 128 && ept == 64 && ctas == 4) FDDM_JUMP_LAUNCH(128, 64, 4);
       else if (NOISE == 2 && nt == 128 && ept == 64) FDDM_JUMP_LAUNCH(128, 64, 3);
-      else if (NOISE == 2 && nt == 256 && ept == 32) FDDM_JUMP_LAUNCH(256, 32, 3);
       else if (nt == 128) FDDM_JUMP_LAUNCH(128, 32, 2);
       else if (nt == 256) FDDM_JUMP_LAUNCH(256, 32, 2);
       else if (ept == 32) FDDM_JUMP_LAUNCH(512, 32, 1);

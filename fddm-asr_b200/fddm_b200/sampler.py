@@ -174,19 +174,52 @@ class DiffusionJumpySampler:
 
     @torch.no_grad()
     def sample(self, cond_c: Tensor, seq_len: int, init: Literal["uniform", "random"] = "uniform", *,
-               x_init: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+               x_init: Optional[Tensor] = None, return_p: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
         """sampler:241-293.  Returns (x_0 ids [B,L], p_x0_last [B,L,K]).
         `x_init` (extra, keyword-only): the initial ids x_T instead of drawing them here (parity tests,
-        CUDA-graph replay with caller-owned state)."""
+        CUDA-graph replay with caller-owned state).  `return_p=False` (extra): the last jump emits only
+        argmax p_x0 -- the ids -- and p_x0_last is None (the evaluation callers drop it: evaluate.py:176,422)."""
         if self._graph_enabled and cond_c.is_cuda and not torch.cuda.is_current_stream_capturing():
-            return self._sample_graphed(cond_c, seq_len, x_init)
-        return self._sample_chain(cond_c, seq_len, x_init)
+            return self._sample_graphed(cond_c, seq_len, x_init, return_p)
+        return self._sample_chain(cond_c, seq_len, x_init, return_p)
 
     @torch.no_grad()
-    def _sample_graphed(self, cond_c: Tensor, seq_len: int, x_init: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    def sample_utterances(self, cond_c: Tensor, seq_len: int, num_samples: int = 1, *,
+                          x_init: Optional[Tensor] = None, return_p: bool = False,
+                          per_utterance_draws: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+        """the batched form of the reference's evaluation loops, which build one B=1
+        sampler per utterance (models/evaluate.py:163-176) and, for multi-sample decoding, per utterance AND per
+        sample (evaluate.py:405-422) -- B (x num_samples) chains of B=1 kernels.  Here all of them are rows of ONE
+        chain: `cond_c[b]` is repeated `num_samples` times and every row has its own x_T and its own draws.
+
+        Returns (ids [B, num_samples, L], p_x0 [B, num_samples, L, K] or None).  The jump kernels are
+        row-independent, so with a row-independent decoder, greedy / "max" decoding gives, for every utterance,
+        exactly the ids of its own B=1 chain started from the same x_T (GPU test
+        `test_sample_utterances_equals_per_utterance_loop`).  `per_utterance_draws=True` draws x_T with one
+        `randint((1, L))` per row, in the loop's order, so the generator is consumed draw for draw like the loop."""
+        if cond_c.dim() < 1 or num_samples < 1:
+            raise ValueError("sample_utterances: cond_c must have a batch axis and num_samples must be >= 1")
+        B = cond_c.size(0)
+        S = int(num_samples)
+        rows = B * S
+        cond_rows = cond_c if S == 1 else cond_c.repeat_interleave(S, dim=0)
+        if x_init is not None:
+            x_T = x_init.reshape(rows, seq_len).long()
+        elif per_utterance_draws:
+            x_T = torch.cat([torch.randint(low=0, high=self.K, size=(1, seq_len), device=cond_c.device,
+                                           generator=self.generator) for _ in range(rows)], dim=0)
+        else:
+            x_T = torch.randint(low=0, high=self.K, size=(rows, seq_len), device=cond_c.device,
+                                generator=self.generator)
+        ids, p = self.sample(cond_rows, seq_len, x_init=x_T, return_p=return_p)
+        return ids.view(B, S, seq_len), (p.view(B, S, seq_len, self.K) if p is not None else None)
+
+    @torch.no_grad()
+    def _sample_graphed(self, cond_c: Tensor, seq_len: int, x_init: Optional[Tensor],
+                        return_p: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
         B = cond_c.size(0)
         dev = cond_c.device
-        key = (tuple(cond_c.shape), cond_c.dtype, int(seq_len), dev.index)
+        key = (tuple(cond_c.shape), cond_c.dtype, int(seq_len), dev.index, bool(return_p))
         # x_T is drawn outside the graph (one tiny kernel, same generator semantics as the eager path)
         x_T = x_init.long() if x_init is not None else torch.randint(low=0, high=self.K, size=(B, seq_len), device=dev,
                                                                       generator=self.generator)
@@ -202,11 +235,11 @@ class DiffusionJumpySampler:
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):                         # warm-up outside capture (lazy init, autotune)
                 for _ in range(2):
-                    self._sample_chain(s_cond, seq_len, s_x)
+                    self._sample_chain(s_cond, seq_len, s_x, return_p)
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self._sample_chain(s_cond, seq_len, s_x)
+                out = self._sample_chain(s_cond, seq_len, s_x, return_p)
             ent = self._graphs[key] = (graph, s_cond, s_x, out)
         graph, s_cond, s_x, out = ent
         s_cond.copy_(cond_c)
@@ -215,7 +248,8 @@ class DiffusionJumpySampler:
         return out
 
     @torch.no_grad()
-    def _sample_chain(self, cond_c: Tensor, seq_len: int, x_init: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    def _sample_chain(self, cond_c: Tensor, seq_len: int, x_init: Optional[Tensor],
+                      return_p: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
         B = cond_c.size(0)
         device = cond_c.device
         if x_init is not None:
@@ -234,13 +268,13 @@ class DiffusionJumpySampler:
             last = (t - delta) <= 0
             # only the last p_x0 is returned, so only the last jump writes it; its argmax (the
             # sampler's final x_0, sampler:292) is fused into the same kernel
-            x_t_idx, p, amax = self._jump(x_t_idx, t, delta, cond_c, seq_len, want_p=last, want_argmax=last,
-                                          step=step)
+            x_t_idx, p, amax = self._jump(x_t_idx, t, delta, cond_c, seq_len, want_p=last and return_p,
+                                          want_argmax=last, step=step)
             if last:
                 p_x0_last, x_0_idx = p, amax
             t -= delta
             step += 1
-        if p_x0_last is None:                                    # T_infer <= 0: the reference fails here too
+        if x_0_idx is None:                                      # T_infer <= 0: the reference fails here too
             raise AttributeError("'NoneType' object has no attribute 'argmax'")
         self.last_resampled_idx = x_t_idx                         # dropped by the reference (Q9); kept for inspection
         return x_0_idx, p_x0_last

@@ -532,6 +532,60 @@ def test_sampler_cuda_graph_chain(fb, greedy):
         assert not torch.equal(a, graphed.last_resampled_idx)
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_sample_utterances_equals_per_utterance_loop(fb, mode):
+    """the reference's evaluation builds one B=1 sampler per utterance (models/evaluate.py:163-176).
+    `sample_utterances` runs all utterances as rows of one chain; with greedy decoding every utterance gets
+    exactly the ids of its own B=1 chain (same x_T), and with injected noise so does every (utterance, sample)."""
+    K, B, L, S = 4000, 5, 24, 3
+    s = make_sched(fb, K, 200)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    base = torch.randn(64, K, generator=g, device="cuda") * 3
+    dirs = torch.randn(4, K, generator=g, device="cuda")
+
+    def dec(x, t, c):                                             # row-independent: depends on the row's x, t and cond
+        pos = torch.arange(x.size(1), device=x.device)
+        return base[(x + 7 * pos) % 64] + c[:, :1, :1] * dirs[pos % 4] + 0.01 * t.view(-1, 1, 1).float()
+
+    cond = torch.randn(B, 3, 5, device="cuda")
+    mk = lambda greedy: fb.DiffusionJumpySampler(s, dec, K=K, T_train=200, T_infer=20, r=5, greedy=greedy,
+                                                 posterior_mode="map", sampling_mode=mode, device=torch.device("cuda"))
+    # greedy, one sample per utterance (evaluate.py:163-176)
+    x_T = torch.randint(0, K, (B, L), generator=g, device="cuda")
+    got, p = mk(True).sample_utterances(cond, L, x_init=x_T)
+    assert got.shape == (B, 1, L) and p is None
+    for b in range(B):
+        want, _ = mk(True).sample(cond[b:b + 1], L, x_init=x_T[b:b + 1])
+        assert torch.equal(got[b, 0], want[0]), b
+    # sampling, S samples per utterance (evaluate.py:405-422), with the exponential noise injected row by row
+    x_T = torch.randint(0, K, (B, S, L), generator=g, device="cuda")
+    E = torch.empty(4, B * S, L, K, device="cuda").exponential_(generator=g)
+    smp = mk(False)
+    smp.noise_fn = lambda step, shape: E[step]
+    got, p = smp.sample_utterances(cond, L, num_samples=S, x_init=x_T, return_p=True)
+    assert got.shape == (B, S, L) and p.shape == (B, S, L, K)
+    for b in range(B):
+        for k in range(S):
+            one = mk(False)
+            one.noise_fn = lambda step, shape, r=b * S + k: E[step, r:r + 1]
+            want, want_p = one.sample(cond[b:b + 1], L, x_init=x_T[b, k:k + 1])
+            assert torch.equal(got[b, k], want[0]), (b, k)
+            assert torch.equal(p[b, k], want_p[0]), (b, k)
+    # in-kernel RNG: shapes, and the samples of one utterance are not copies of each other; draw-for-draw x_T
+    smp = mk(False)
+    smp.generator = torch.Generator(device="cuda").manual_seed(9)
+    got, _ = smp.sample_utterances(cond, L, num_samples=S, per_utterance_draws=True)
+    assert got.shape == (B, S, L)
+    assert not torch.equal(smp.last_resampled_idx.view(B, S, L)[:, 0], smp.last_resampled_idx.view(B, S, L)[:, 1])
+    ref_gen = torch.Generator(device="cuda").manual_seed(9)
+    first = torch.randint(low=0, high=K, size=(1, L), device="cuda", generator=ref_gen)
+    smp2 = mk(True)
+    smp2.generator = torch.Generator(device="cuda").manual_seed(9)
+    a, _ = smp2.sample_utterances(cond, L, per_utterance_draws=True)
+    b1, _ = mk(True).sample(cond[:1], L, x_init=first)
+    assert torch.equal(a[0, 0], b1[0])
+
+
 def test_jump_philox_offsets_advance_per_jump(fb):
     """Two consecutive sampling jumps driven by one device-side {seed, offset} draw DIFFERENT variates (the
     offset is advanced on the device after every jump), and a sample_q call sharing that state is independent

@@ -296,7 +296,7 @@ class ResidentDecoder:
         return self.logits
 
 
-def shard_check(fb, dev, group, world, rank, per_rank_b=8):
+def shard_check(fb, dev, group, world, rank, per_rank_b=8, collective="nccl"):
     """world>1 only: the batch-sharded kl_term / lfd_loss (values AND gradients, through the same host classes
     the timed step uses) must equal this library's single-process evaluation of the whole batch (which the
     -m gpu parity tests pin to the oracle).  Small batch; every rank builds the same global batch.
@@ -319,7 +319,7 @@ def shard_check(fb, dev, group, world, rank, per_rank_b=8):
     (kl_ref + 0.5 * lf_ref).backward()
     lgs = logits[sl].clone().requires_grad_(True); a_s = za[sl].clone().requires_grad_(True); b_s = zb[sl].clone().requires_grad_(True)
     kl = fb.SchedulerAdapter(sch, group=group).kl_term(xt[sl], x0[sl], lgs, t[sl], mask[sl])
-    op = fb.LfdPipeline(a_s, b_s, LAMBDA, group=group)
+    op = fb.LfdPipeline(a_s, b_s, LAMBDA, group=group, collective=collective)
     op.stats(); op.xcov()
     lf = op.loss()
     (kl + 0.5 * lf).backward()
@@ -412,12 +412,43 @@ def run_gpu(args):
     if args.gpus != world and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torchrun", file=sys.stderr)
 
+    # How the three L_fd exchange buffers are summed over the ranks: ncclAllReduce, or the library's own kernel on
+    # symmetric memory ("p2p": peer loads/stores; "nvls": in-switch multicast reduction).  "auto" takes p2p when
+    # every rank can set up symmetric memory, NCCL otherwise.
+    exchange = "nccl"
+    if world > 1 and args.exchange != "nccl":
+        if args.exchange == "auto":
+            if fb.symmetric_exchange_available(group, multicast=True):
+                exchange = "nvls"
+            elif world in (2, 4, 8) and fb.symmetric_exchange_available(group):
+                exchange = "p2p"
+        elif not fb.symmetric_exchange_available(group, multicast=(args.exchange == "nvls")):
+            raise SystemExit(f"bench.py: --exchange {args.exchange} needs symmetric memory"
+                             + (" with a multicast mapping" if args.exchange == "nvls" else "") + ", not available here")
+        else:
+            exchange = args.exchange
+    # SMs left free by the persistent row kernels for the exchange kernels that run under them (overlap mode):
+    # NCCL needs its 16 CTAs (4 / 8 / 16 / 24 / 32 measured at N=8); the library's own kernel is as fast with 8
+    # (N=4, c5: 911 G tok*V/s with 8 reserved SMs vs 887 with 16, profiles/r02k_xgpu_exchange.md)
+    reserve_sms = nccl_ctas if exchange == "nccl" else int(os.environ.get("FDDM_XGPU_CTAS", "8"))
+    def shard_checks(collective):
+        res = shard_check(fb, dev, group, world, rank, per_rank_b=32, collective=collective)   # the path the timed step takes
+        if res["ok"]:
+            small = shard_check(fb, dev, group, world, rank, per_rank_b=8, collective=collective)   # and the small-batch path
+            res = {**res, "small_batch_path": small, "ok": small["ok"]}
+        res["exchange"] = collective
+        return res
+
     shard = None
     if world > 1:
-        shard = shard_check(fb, dev, group, world, rank, per_rank_b=32)      # the path the timed step takes
-        if shard["ok"]:
-            small = shard_check(fb, dev, group, world, rank, per_rank_b=8)   # and the small-batch path
-            shard = {**shard, "small_batch_path": small, "ok": small["ok"]}
+        shard = shard_checks(exchange)
+        if not shard["ok"] and args.exchange == "auto" and exchange != "nccl":
+            if rank == 0:
+                print(f"bench.py: shard_check failed with --exchange {exchange} ({shard}); falling back to NCCL",
+                      file=sys.stderr, flush=True)
+            failed, exchange = shard, "nccl"
+            reserve_sms = nccl_ctas
+            shard = {**shard_checks(exchange), "own_kernel_exchange_failed": failed}
         if not shard["ok"]:
             if rank == 0:
                 print(json.dumps({"error": "shard_check failed: the batch-sharded path disagrees with the whole-batch "
@@ -439,7 +470,9 @@ def run_gpu(args):
         d[k].requires_grad_(kind == "train")
 
     if overlap:
-        fb.set_sm_reserve(nccl_ctas)
+        fb.set_sm_reserve(reserve_sms)
+        if exchange != "nccl":
+            fb.losses._SymmExchange.of(group).max_ctas = reserve_sms
     sch = fb.DiscreteDiffusionScheduler(K=V, T=T_TRAIN, device=dev)
     # multi-GPU: the KL scalar is folded into the one scalar all-reduce at the end of the step
     ad = fb.SchedulerAdapter(sch, group=group, defer_reduce=(D > 0))
@@ -463,7 +496,7 @@ def run_gpu(args):
             dd[k].grad = None
         lfd_op = None
         if D > 0:
-            lfd_op = fb.LfdPipeline(dd["za"], dd["zb"], LAMBDA, group=group, overlap=overlap)
+            lfd_op = fb.LfdPipeline(dd["za"], dd["zb"], LAMBDA, group=group, overlap=overlap, collective=exchange)
             lfd_op.stats()                                        # + all-reduce of the batch statistics
         pstate[1:].add_(8)
         xt = ad.sample_q(dd["x0"], dd["t"], philox_state=pstate)
@@ -688,8 +721,9 @@ def run_gpu(args):
                                    + (" (BASELINE configs[4], batch-sharded)" if args.workload == "c5" else "")
                                    + f"; step = {what}",
                        "global_batch": Bg, "seq_len": L, "vocab": V, "d_proj": D, "T": T_TRAIN,
-                       "parallelism": f"batch-sharded x{world}" + (" (NCCL all-reduce: KL scalar, L_fd stats/cov/bn sums"
-                                                                     + (f"; the two forward all-reduces overlap the KL / jump kernels, {nccl_ctas} SMs reserved" if overlap else "")
+                       "parallelism": f"batch-sharded x{world}" + ((" (NCCL all-reduce: KL scalar, L_fd stats/cov/bn sums" if exchange == "nccl" else
+                                                                      f" (the library's own {exchange} all-reduce kernel on symmetric memory: L_fd stats / cov + KL scalar / bn sums")
+                                                                     + (f"; the two forward all-reduces overlap the KL / jump kernels, {reserve_sms} SMs reserved" if overlap else "")
                                                                      + ")" if world > 1 else ""),
                        "sampling_mode": smp.sampling_mode, "greedy": smp.greedy,
                        "l2": f"inputs {h2d / 1e6:.0f} MB/step per GPU > 126 MB L2 (no flush needed)"},
@@ -776,6 +810,9 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--sampling-mode", default="exact", choices=["exact", "fast"], help="c3 only")
     ap.add_argument("--greedy", action="store_true", help="c3 only: argmax instead of Categorical")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "nvls"],
+                    help="N>1: how the L_fd exchange buffers are summed: ncclAllReduce, or the library's own kernel on "
+                         "symmetric memory (p2p: peer loads/stores; nvls: in-switch multicast reduction)")
     ap.add_argument("--collectives", default="auto", choices=["auto", "overlap", "serial"],
                     help="N>1: run L_fd's forward all-reduces under the KL / jump kernels (side stream) or in order")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and eager_b200 legs")

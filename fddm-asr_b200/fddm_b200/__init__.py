@@ -13,8 +13,9 @@ from ._lib import set_sm_reserve
 from .scheduler import DiscreteDiffusionScheduler
 from .adapter import SchedulerAdapter
 from .sampler import DiffusionJumpySampler, ModelAdapter
-from .losses import LfdPipeline, lfd_loss
+from . import losses
+from .losses import LfdPipeline, lfd_loss, symmetric_exchange_available
 from .metrics import batch_cer, batch_wer, calculate_cer, calculate_wer
 
 __all__ = ["DiscreteDiffusionScheduler", "SchedulerAdapter", "DiffusionJumpySampler", "ModelAdapter", "lfd_loss", "LfdPipeline",
-           "_lib", "set_sm_reserve", "calculate_cer", "calculate_wer", "batch_cer", "batch_wer"]
+           "_lib", "set_sm_reserve", "symmetric_exchange_available", "calculate_cer", "calculate_wer", "batch_cer", "batch_wer"]

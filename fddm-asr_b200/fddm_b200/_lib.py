@@ -23,6 +23,7 @@ F32, BF16, F16 = 0, 1, 2
 JUMP_EXACT, JUMP_SAMPLE, JUMP_WRITE_P, JUMP_DEBUG_W = 0x1, 0x2, 0x4, 0x8
 LFD_PLANES_VALID = 0x2
 KL_MASK_F32, KL_CLAMP_T = 0x1, 0x2
+XGPU_P2P, XGPU_NVLS = 1, 2
 MAX_VOCAB = 49152
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
@@ -59,6 +60,8 @@ SIGNATURES = {
                               _vp, _vp, _vp, _vp, _vp, _vp]),
     "fddm_edit_distance_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "fddm_edit_distance": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "fddm_xgpu_signal_pad_bytes": (_i64, []),
+    "fddm_xgpu_allreduce": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _i32, _vp]),
     "fddm_lfd_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64]),
     "fddm_lfd_stats": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp]),
     "fddm_lfd_xcov": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _f64, _f32, _vp, _vp, _vp]),

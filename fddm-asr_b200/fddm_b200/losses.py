@@ -33,36 +33,117 @@ from . import _lib as L
 _comm_streams = {}
 
 
-def _comm_stream(dev: torch.device) -> torch.cuda.Stream:
-    s = _comm_streams.get(dev.index)
-    if s is None:
-        # high priority: the collective's few CTAs are placed ahead of the queued CTAs of the persistent
-        # row kernels (whose dynamic row scheduler simply runs with fewer resident CTAs meanwhile)
-        s = _comm_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
-    return s
+class _SymmExchange:
+    """Symmetric-memory exchange buffers of one process group: the three L_fd exchange
+    arrays live in `torch.distributed._symmetric_memory` allocations (every rank has every peer's copy mapped over
+    NVLink / NVSwitch) and are summed over the ranks IN PLACE by the library's own kernel (`fddm_xgpu_allreduce`:
+    peer loads / stores of a 1/world slice, or multimem.ld_reduce / multimem.st through the switch) instead of
+    ncclAllReduce.  Buffers are cached per (name, length, dtype) and reused by every step; `gen` counts the
+    re-uses so that a backward whose saved statistics were overwritten by a later forward fails loudly."""
+
+    _by_group = {}
+
+    def __init__(self, group):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.group = group
+        self.group_name = group.group_name
+        self.rank = torch.distributed.get_rank(group)
+        self.world = torch.distributed.get_world_size(group)
+        self.bufs = {}
+        self.gen = {}
+        self.max_ctas = 0           # 0: library default; set to the reserved SM count when overlapping (set_sm_reserve)
+
+    @classmethod
+    def of(cls, group) -> "_SymmExchange":
+        ex = cls._by_group.get(group.group_name)
+        if ex is None:
+            ex = cls._by_group[group.group_name] = cls(group)
+        return ex
+
+    def buffer(self, name: str, numel: int, dtype: torch.dtype, dev: torch.device):
+        """(tensor of `numel` elements, key); the allocation is padded to a multiple of 4 elements (zero pad).
+        The first call for a key is COLLECTIVE (rendezvous) and must not happen inside a stream capture."""
+        key = (name, int(numel), dtype, dev.index)
+        ent = self.bufs.get(key)
+        if ent is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("lfd_loss(collective='p2p'|'nvls'): run one eager step before capturing a CUDA graph "
+                                   "(the symmetric buffers are allocated collectively on first use)")
+            padded = (int(numel) + 3) // 4 * 4
+            t = self.symm.empty(padded, dtype=dtype, device=dev)
+            t.zero_()
+            hdl = self.symm.rendezvous(t, self.group_name)
+            if self.world not in (2, 4, 8) and not int(hdl.multicast_ptr):
+                raise RuntimeError("the peer-to-peer all-reduce is built for 2, 4 or 8 ranks")
+            if int(hdl.signal_pad_size) < int(L.lib.fddm_xgpu_signal_pad_bytes()):
+                raise RuntimeError("symmetric-memory signal pad is too small")
+            ent = self.bufs[key] = (t, hdl, padded)
+            self.gen[key] = 0
+        self.gen[key] += 1
+        return ent[0][:numel], key
+
+    def all_reduce(self, key, algo: str = "p2p"):
+        t, hdl, padded = self.bufs[key]
+        mc = int(hdl.multicast_ptr)
+        code = L.XGPU_NVLS if (algo == "nvls" and mc) or self.world not in (2, 4, 8) else L.XGPU_P2P
+        L.check(L.lib.fddm_xgpu_allreduce(int(hdl.buffer_ptrs_dev), mc or None, int(hdl.signal_pad_ptrs_dev),
+                                          self.rank, self.world, t.element_size(), padded, code, int(self.max_ctas),
+                                          L.stream_ptr(t.device)), "xgpu_allreduce")
+
+
+def symmetric_exchange_available(group=None, multicast: bool = False) -> bool:
+    """True when every rank of `group` can allocate and rendezvous symmetric memory -- with `multicast=True`, also
+    with a multicast (NVLS) mapping -- i.e. when `lfd_loss(..., collective="p2p")` (resp. "nvls") can be used.
+    Collective call: every rank must make it."""
+    if not torch.distributed.is_initialized():
+        return False
+    group = group or torch.distributed.group.WORLD
+    if torch.distributed.get_world_size(group) < 2:
+        return False
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ok = 1
+    try:
+        ex = _SymmExchange.of(group)
+        _, key = ex.buffer("probe", 4, torch.float32, dev)
+        if multicast and not int(ex.bufs[key][1].multicast_ptr):
+            ok = 0
+    except Exception:                                            # noqa: BLE001 -- any failure means "not available"
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
+    return bool(int(flag))
 
 
 class _AsyncAllReduce:
     """SUM all-reduce of `x` on the side stream; `wait()` makes the current stream wait for it.
-    With group None both calls are no-ops."""
+    With group None both calls are no-ops.  `symm` = (exchange, key): `x` is that symmetric buffer and the
+    library's own kernel (`algo`: "p2p" or "nvls") does the reduction instead of NCCL."""
 
-    def __init__(self, x: torch.Tensor, group, overlap: bool):
+    def __init__(self, x: torch.Tensor, group, overlap: bool, symm=None, algo: str = "p2p"):
         self.done = None
         if group is None:
             return
+
+        def reduce():
+            if symm is not None:
+                symm[0].all_reduce(symm[1], algo)
+            else:
+                torch.distributed.all_reduce(x, op=torch.distributed.ReduceOp.SUM, group=group)
+
         if not overlap:
-            torch.distributed.all_reduce(x, op=torch.distributed.ReduceOp.SUM, group=group)
+            reduce()
             return
         dev = x.device
         cur = torch.cuda.current_stream(dev)
         comm = _comm_stream(dev)
         ready = torch.cuda.Event()
         ready.record(cur)
-        if not torch.cuda.is_current_stream_capturing():        # (a captured graph keeps its pool alive itself)
+        if symm is None and not torch.cuda.is_current_stream_capturing():   # (a captured graph keeps its pool alive)
             x.record_stream(comm)
         with torch.cuda.stream(comm):
             comm.wait_event(ready)
-            torch.distributed.all_reduce(x, op=torch.distributed.ReduceOp.SUM, group=group)
+            reduce()
             self.done = torch.cuda.Event()
             self.done.record(comm)
 
@@ -96,14 +177,18 @@ class _LfdLossFn(torch.autograd.Function):
             G[:dv, :dv] = G_v.view(dv, dv)
             G = G.view(-1)
         ctx.save_for_backward(z_a, z_b, op.sums, G, op.ws)
-        ctx.meta = (B, T, D, op.dt, op.world, op.eps, op.group, op.private_ws)
+        ctx.meta = (B, T, D, op.dt, op.world, op.eps, op.group, op.private_ws, op.exchange, op.sums_gen, op.collective)
         return loss.to(z_a.dtype)                              # the reference's result has the input dtype
 
     @staticmethod
     def backward(ctx, grad_out):
         z_a, z_b, sums, G, ws = ctx.saved_tensors
-        B, T, D, dt, world, eps, group, private_ws = ctx.meta
+        B, T, D, dt, world, eps, group, private_ws, exchange, sums_gen, collective = ctx.meta
         dev = z_a.device
+        if exchange is not None and exchange.gen[sums_gen[0]] != sums_gen[1]:
+            raise RuntimeError("lfd_loss(collective='p2p'|'nvls'): the shared exchange buffer holding this call's batch "
+                               "statistics was overwritten by a later lfd_loss forward of the same shape; run "
+                               "backward before the next forward, or use collective='nccl'")
         st = L.stream_ptr(dev)
         parts = int(L.lib.fddm_lfd_bn_parts(B, T, D))
         bn = torch.empty(2 * T * parts * D, dtype=torch.float32, device=dev)
@@ -120,10 +205,19 @@ class _LfdLossFn(torch.autograd.Function):
             # Only sum_b dz~*z~ crosses ranks, in fp32: [2][T][D].  (The other batch-norm moment, sum_b dz~ =
             # sum_k (sum_b z~[b,t,k]) G[.,k] / N, is identically zero over the GLOBAL batch because z~ has zero
             # global batch mean; the library never computes it.)
-            if parts > 1:
-                bn = bn.view(2 * T, parts, D).sum(dim=1).contiguous()
-                parts = 1
-            torch.distributed.all_reduce(bn, op=torch.distributed.ReduceOp.SUM, group=group)
+            if exchange is not None:
+                xb, key = exchange.buffer("bn", 2 * T * D, torch.float32, dev)
+                if parts > 1:
+                    torch.sum(bn.view(2 * T, parts, D), dim=1, out=xb.view(2 * T, D))
+                else:
+                    xb.copy_(bn)
+                exchange.all_reduce(key, collective)
+                bn, parts = xb, 1
+            else:
+                if parts > 1:
+                    bn = bn.view(2 * T, parts, D).sum(dim=1).contiguous()
+                    parts = 1
+                torch.distributed.all_reduce(bn, op=torch.distributed.ReduceOp.SUM, group=group)
         L.check(L.lib.fddm_lfd_backward(*args, bn.data_ptr(), parts, 1, dz_a.data_ptr(), dz_b.data_ptr(), st),
                 "lfd_backward[1]")
         return dz_a, dz_b, None
@@ -131,7 +225,7 @@ class _LfdLossFn(torch.autograd.Function):
 
 class LfdPipeline:
     def __init__(self, z_a: torch.Tensor, z_b: torch.Tensor, lambda_offdiag: float = 5.0e-3, eps: float = 1e-5, *,
-                 group=None, overlap: bool = False):
+                 group=None, overlap: bool = False, collective: str = "nccl"):
         if z_a.dim() != 3:
             raise ValueError(f"z_a must be (B, T, D), got shape {tuple(z_a.shape)}")
         B, T, D = z_a.shape
@@ -152,6 +246,12 @@ class LfdPipeline:
         self.lam, self.eps, self.group = float(lambda_offdiag), float(eps), group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
         self.overlap = overlap
+        if collective not in ("nccl", "p2p", "nvls"):
+            raise ValueError("collective must be 'nccl', 'p2p' or 'nvls'")
+        # "p2p" / "nvls": the exchange buffers are symmetric memory, summed by the library's own kernel
+        self.collective = collective
+        self.exchange = _SymmExchange.of(group) if (collective != "nccl" and self.world > 1) else None
+        self.sums_gen = None
         self.shape = (B, T, D)
         nbytes = int(L.lib.fddm_lfd_workspace_bytes(B, T, D))
         self.private_ws = torch.is_grad_enabled() and (z_a.requires_grad or z_b.requires_grad)
@@ -169,11 +269,17 @@ class LfdPipeline:
 
     def stats(self):
         B, T, D = self.shape
-        self.sums = torch.empty(4 * T * D, dtype=torch.float64, device=self.dev)
+        symm = None
+        if self.exchange is not None:
+            self.sums, key = self.exchange.buffer("sums", 4 * T * D, torch.float64, self.dev)
+            self.sums_gen = (key, self.exchange.gen[key])
+            symm = (self.exchange, key)
+        else:
+            self.sums = torch.empty(4 * T * D, dtype=torch.float64, device=self.dev)
         za, zb = self.z_a.detach(), self.z_b.detach()
         L.check(L.lib.fddm_lfd_stats(za.data_ptr(), zb.data_ptr(), self.dt, B, T, D, self.sums.data_ptr(),
                                      L.stream_ptr(self.dev)), "lfd_stats")
-        self._ar_sums = _AsyncAllReduce(self.sums, self.group, self.overlap)
+        self._ar_sums = _AsyncAllReduce(self.sums, self.group, self.overlap, symm, self.collective)
         return self
 
     def xcov(self, piggyback: torch.Tensor = None):
@@ -184,7 +290,12 @@ class LfdPipeline:
             self.stats()
         B, T, D = self.shape
         self._ar_sums.wait()
-        self.cov = torch.empty(D * D + 1, dtype=torch.float32, device=self.dev)
+        symm = None
+        if self.exchange is not None:
+            self.cov, key = self.exchange.buffer("cov", D * D + 1, torch.float32, self.dev)
+            symm = (self.exchange, key)
+        else:
+            self.cov = torch.empty(D * D + 1, dtype=torch.float32, device=self.dev)
         if piggyback is not None:
             self.cov[D * D:].copy_(piggyback.detach().reshape(1))
         else:
@@ -193,7 +304,7 @@ class LfdPipeline:
         L.check(L.lib.fddm_lfd_xcov(za.data_ptr(), zb.data_ptr(), self.dt, B, T, D, self.sums.data_ptr(),
                                     float(B * self.world), self.eps, self.ws.data_ptr(), self.cov.data_ptr(),
                                     L.stream_ptr(self.dev)), "lfd_xcov")
-        self._ar_cov = _AsyncAllReduce(self.cov, self.group, self.overlap)
+        self._ar_cov = _AsyncAllReduce(self.cov, self.group, self.overlap, symm, self.collective)
         return self
 
     def loss(self) -> torch.Tensor:
@@ -205,7 +316,10 @@ class LfdPipeline:
 
 
 def lfd_loss(z_a: torch.Tensor, z_b: torch.Tensor, lambda_offdiag: float = 5.0e-3, eps: float = 1e-5, *,
-             group=None) -> torch.Tensor:
+             group=None, collective: str = "nccl") -> torch.Tensor:
     """`group`: optional torch.distributed process group over which the batch axis is sharded; the
-    loss (and its gradients) are then those of the reference evaluated on the global batch."""
-    return LfdPipeline(z_a, z_b, lambda_offdiag, eps, group=group, overlap=False).loss()
+    loss (and its gradients) are then those of the reference evaluated on the global batch.
+    `collective`: "nccl" (ncclAllReduce), or "p2p" / "nvls": symmetric-memory buffers summed by the library's own
+    `fddm_xgpu_allreduce` kernel (peer loads/stores, or in-switch multicast reduction); both need
+    `symmetric_exchange_available(group)`."""
+    return LfdPipeline(z_a, z_b, lambda_offdiag, eps, group=group, overlap=False, collective=collective).loss()

@@ -236,6 +236,32 @@ int fddm_edit_distance(const int32_t* ref, const int64_t* ref_off, const int32_t
                        const int64_t* hyp_off, int64_t n_pairs, int64_t max_hyp_len, void* workspace,
                        int32_t* dist_out, fddm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (e) multi-GPU exchange of the batch-sharded L_fd                     SURVEY.md section 8(e)
+ * The library's own SUM all-reduce, in place, of a buffer that lives in symmetric memory (every rank has every
+ * peer's copy mapped over NVLink / NVSwitch): one kernel, two cross-GPU flag barriers, no NCCL.  Replaces
+ * ncclAllReduce for the three 1.6-6.3 MB exchanges of losses/fddm_losses.py's statistics when the batch is sharded
+ * (the reference itself has no multi-GPU path).
+ *   FDDM_XGPU_P2P   each rank loads its 1/world slice from every copy (summed in rank order: bitwise the same
+ *                   result on every rank) and stores the sums into every copy.  world 2, 4 or 8.
+ *   FDDM_XGPU_NVLS  the slice is reduced and re-broadcast by the switch (multimem.ld_reduce / multimem.st)
+ *                   through the multicast mapping.
+ *   buffer_ptrs_dev      DEVICE array [world] of pointers to the ranks' copies (P2P), 16-byte aligned
+ *   multicast_ptr        multicast address of the buffer (NVLS), or NULL
+ *   signal_pad_ptrs_dev  DEVICE array [world] of pointers to the ranks' signal pads, each at least
+ *                        fddm_xgpu_signal_pad_bytes() long and zero before first use; the library uses bytes
+ *                        [4096, fddm_xgpu_signal_pad_bytes()) only
+ *   elem_bytes           4 (fp32) or 8 (fp64); n * elem_bytes must be a multiple of 16
+ *   max_ctas             upper bound on the CTAs of the kernel (0: the default, 32) -- the number of SMs to
+ *                        reserve with fddm_set_sm_reserve when it runs under a persistent row kernel
+ * Every rank must make the same call (same n, algo, max_ctas) in the same order; stream-ordered, CUDA-graph
+ * capturable. */
+#define FDDM_XGPU_P2P 1
+#define FDDM_XGPU_NVLS 2
+int64_t fddm_xgpu_signal_pad_bytes(void);
+int fddm_xgpu_allreduce(const void* buffer_ptrs_dev, void* multicast_ptr, const void* signal_pad_ptrs_dev, int rank,
+                        int world, int elem_bytes, int64_t n, int algo, int max_ctas, fddm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,11 +23,18 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for per_rank_b in (8, 32, 40):
-        res = bench.shard_check(fb, dev, dist.group.WORLD, world, rank, per_rank_b=per_rank_b)
-        ok = ok and res["ok"]
-        if rank == 0:
-            print("multi-gpu check", "OK" if res["ok"] else "FAILED", "world", world, json.dumps(res), flush=True)
+    modes = ["nccl"]
+    if fb.symmetric_exchange_available(dist.group.WORLD):        # the library's own all-reduce kernels
+        modes += ["p2p", "nvls"]
+    elif rank == 0:
+        print("multi-gpu check: symmetric memory not available here, only the NCCL exchange is checked", flush=True)
+    for collective in modes:
+        for per_rank_b in (8, 32, 40):
+            res = bench.shard_check(fb, dev, dist.group.WORLD, world, rank, per_rank_b=per_rank_b, collective=collective)
+            ok = ok and res["ok"]
+            if rank == 0:
+                print("multi-gpu check", "OK" if res["ok"] else "FAILED", "world", world, "exchange", collective,
+                      json.dumps(res), flush=True)
     bench.teardown(world, dev, code=0 if ok else 1)
 
 

@@ -110,6 +110,16 @@ def test_host_only_entry_points():
     assert lib.fddm_set_sm_reserve(-1) == -1 and b"set_sm_reserve" in lib.fddm_last_error()
     rc = lib.fddm_edit_distance(None, None, None, None, 1, 4, None, None, None)
     assert rc == -1 and b"null" in lib.fddm_last_error()
+    # the library's own all-reduce: pad size, and argument validation before any CUDA call
+    assert lib.fddm_xgpu_signal_pad_bytes() == 4096 + (32 * 16 + 32) * 4
+    L = fddm_b200._lib
+    assert lib.fddm_xgpu_allreduce(None, None, None, 0, 2, 4, 16, L.XGPU_P2P, 0, None) == -1          # no signal pads
+    assert lib.fddm_xgpu_allreduce(8, None, 8, 0, 1, 4, 16, L.XGPU_P2P, 0, None) == -1 and b"world" in lib.fddm_last_error()
+    assert lib.fddm_xgpu_allreduce(8, None, 8, 0, 2, 4, 18, L.XGPU_P2P, 0, None) == -1 and b"16 bytes" in lib.fddm_last_error()
+    assert lib.fddm_xgpu_allreduce(8, None, 8, 0, 2, 2, 16, L.XGPU_P2P, 0, None) == -1 and b"elem_bytes" in lib.fddm_last_error()
+    assert lib.fddm_xgpu_allreduce(None, None, 8, 0, 2, 8, 16, L.XGPU_NVLS, 0, None) == -1 and b"multicast" in lib.fddm_last_error()
+    assert lib.fddm_xgpu_allreduce(8, None, 8, 0, 2, 8, 16, 7, 0, None) == -1 and b"algorithm" in lib.fddm_last_error()
+    assert not fddm_b200.symmetric_exchange_available()              # no process group here
     # the measurement aid works without a device: nothing recorded -> empty report
     fddm_b200._lib.profile_enable(True)
     assert fddm_b200._lib.profile_read() == {}

@@ -831,3 +831,21 @@ def test_cer_wer_batched_edit_distance(fb):
 def test_lfd_shape_assert(fb):
     with pytest.raises(AssertionError):
         fb.lfd_loss(torch.zeros(2, 3, 8, device="cuda"), torch.zeros(2, 3, 16, device="cuda"))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (one process per GPU)")
+def test_batch_sharded_exchange_modes_two_gpus():
+    """SURVEY 8(e) on hardware: with the batch sharded over two processes, kl_term / lfd_loss (values and
+    gradients) equal the whole-batch evaluation for every exchange mode -- ncclAllReduce and, where the box offers
+    symmetric memory, the library's own all-reduce kernels (fddm_xgpu_allreduce, p2p and NVLS).  Runs
+    scripts/check_multi_gpu.py under torchrun (per-rank batches 8, 32 and 40)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "check_multi_gpu.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("multi-gpu check")]
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert len([ln for ln in lines if " OK " in ln]) >= 3 and not [ln for ln in lines if "FAILED" in ln], lines

@@ -115,6 +115,15 @@ def symmetric_exchange_available(group=None, multicast: bool = False) -> bool:
     return bool(int(flag))
 
 
+def _comm_stream(dev: torch.device) -> torch.cuda.Stream:
+    s = _comm_streams.get(dev.index)
+    if s is None:
+        # high priority: the collective's few CTAs are placed ahead of the queued CTAs of the persistent
+        # row kernels (whose dynamic row scheduler simply runs with fewer resident CTAs meanwhile)
+        s = _comm_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+    return s
+
+
 class _AsyncAllReduce:
     """SUM all-reduce of `x` on the side stream; `wait()` makes the current stream wait for it.
     With group None both calls are no-ops.  `symm` = (exchange, key): `x` is that symmetric buffer and the

@@ -126,6 +126,38 @@ def test_host_only_entry_points():
     fddm_b200._lib.profile_enable(False)
 
 
+def test_no_undefined_names_in_host_code():
+    """The multi-GPU branches of the host mirror and of bench.py only execute on a multi-GPU box; a name that a
+    refactor dropped would first be noticed there.  A small AST walk (names loaded but never bound anywhere in the
+    module, builtins aside) catches that class of mistake here."""
+    import ast
+    import builtins
+    import glob
+    files = (glob.glob(os.path.join(ROOT, "fddm-asr_b200", "fddm_b200", "*.py")) + glob.glob(os.path.join(ROOT, "scripts", "*.py"))
+             + glob.glob(os.path.join(ROOT, "fddm-asr_b200", "dropin", "**", "*.py"), recursive=True)
+             + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")])
+    assert len(files) > 12
+    for path in files:
+        tree = ast.parse(open(path).read())
+        bound = set(dir(builtins)) | {"__file__"}
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.FunctionDef, ast.ClassDef, ast.AsyncFunctionDef)):
+                bound.add(node.name)
+            elif isinstance(node, ast.Import):
+                bound.update((a.asname or a.name).split(".")[0] for a in node.names)
+            elif isinstance(node, ast.ImportFrom):
+                bound.update(a.asname or a.name for a in node.names)
+            elif isinstance(node, ast.Name) and isinstance(node.ctx, (ast.Store, ast.Del)):
+                bound.add(node.id)
+            elif isinstance(node, ast.arg):
+                bound.add(node.arg)
+            elif isinstance(node, ast.ExceptHandler) and node.name:
+                bound.add(node.name)
+        missing = sorted({(n.id, n.lineno) for n in ast.walk(tree)
+                          if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in bound})
+        assert not missing, f"{path}: names used but never bound: {missing}"
+
+
 def test_metrics_host_logic_rejects_cpu_only_runs():
     """calculate_cer / calculate_wer mirror models/evaluate.py:94-134; like every op of the package they have no
     CPU fallback (the oracle restatement lives in oracle/fddm_oracle.py and is pinned by test_oracle_golden.py)."""

@@ -395,17 +395,18 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
-    # Running L_fd's forward all-reduces under the KL / jump kernels costs those kernels the reserved SMs (16 of
-    # 148 = 11 % of their time, which grows with the per-GPU batch) and hides a constant ~90 us: it pays below
-    # roughly 40k token rows per GPU (N >= 4 on c5), not above (N = 2: 65k rows).
+    # Running L_fd's forward exchanges under the KL / jump kernels costs those kernels the reserved SMs and hides a
+    # roughly constant latency.  With NCCL (16 SMs = 11 % of the row kernels' time, ~90 us hidden) it pays below
+    # roughly 40k token rows per GPU (N >= 4 on c5), not above (N = 2: 65k rows).  With the library's own exchange
+    # kernel (8 SMs) it pays at every N measured (N = 2: 2.115 vs 2.137 ms/step).  Decided below, once the exchange
+    # mode is known.
     rows_per_gpu = shape_of(args.workload, world)[0] * shape_of(args.workload, world)[1]
-    overlap = world > 1 and (args.collectives == "overlap" or (args.collectives == "auto" and rows_per_gpu <= 40960))
     nccl_ctas = int(os.environ.get("NCCL_MAX_CTAS", "16"))        # 4 / 8 / 16 / 24 / 32 measured at N=8: 16 is best
     if world > 1:
         import torch.distributed as dist
-        if overlap:
-            # the two forward all-reduces of L_fd run on a side stream under the KL / jump kernels: NCCL is held to
-            # a few CTAs and the persistent row kernels leave exactly that many SMs free
+        if args.collectives != "serial":
+            # an exchange that runs on a side stream under the row kernels is held to a few CTAs, and the persistent
+            # row kernels leave exactly that many SMs free
             os.environ.setdefault("NCCL_MAX_CTAS", str(nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
@@ -431,6 +432,8 @@ def run_gpu(args):
     # NCCL needs its 16 CTAs (4 / 8 / 16 / 24 / 32 measured at N=8); the library's own kernel is as fast with 8
     # (N=4, c5: 911 G tok*V/s with 8 reserved SMs vs 887 with 16, profiles/r02k_xgpu_exchange.md)
     reserve_sms = nccl_ctas if exchange == "nccl" else int(os.environ.get("FDDM_XGPU_CTAS", "8"))
+    overlap = world > 1 and (args.collectives == "overlap" or
+                             (args.collectives == "auto" and (exchange != "nccl" or rows_per_gpu <= 40960)))
     def shard_checks(collective):
         res = shard_check(fb, dev, group, world, rank, per_rank_b=32, collective=collective)   # the path the timed step takes
         if res["ok"]:
@@ -448,6 +451,7 @@ def run_gpu(args):
                       file=sys.stderr, flush=True)
             failed, exchange = shard, "nccl"
             reserve_sms = nccl_ctas
+            overlap = args.collectives == "overlap" or (args.collectives == "auto" and rows_per_gpu <= 40960)
             shard = {**shard_checks(exchange), "own_kernel_exchange_failed": failed}
         if not shard["ok"]:
             if rank == 0:

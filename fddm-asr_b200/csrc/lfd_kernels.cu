@@ -72,30 +72,34 @@ __global__ void __launch_bounds__(256) lfd_stats_kernel(const T* __restrict__ za
   }
 }
 
-// Same moments, one CTA per (position t, strip of 64 column vectors, tensor): thread (tx, ty) owns column vector
-// tx and the batch rows ty, ty+4, ...; the four row groups are combined through shared memory in a fixed order
-// and written directly -- no atomics, no memset, and per thread U 16-byte loads in flight at a 1 KB stride
-// pattern DRAM likes.  Needs D % N == 0 and 16-byte aligned inputs.  grid = (ceil(D/(64 N)), T, 2).
-template <typename T>
+// Same moments, one CTA per (position t, strip of CW column vectors, tensor): thread (tx, ty) owns column vector
+// tx and the batch rows ty, ty+RG, ...; the RG row groups are combined through shared memory in a fixed order
+// and written directly -- no atomics, no memset, and per thread U 16-byte loads in flight at a stride pattern DRAM
+// likes.  CW * RG = 256 threads.  <64, 4, 4> for long batches; <32, 8, 8> for B <= 128, where a thread's whole
+// share of the batch (<= 16 rows) is then at most two rounds of loads instead of four and there are twice as
+// many CTAs to hide the round trips (measured at B=64: 29-33 us against 31-38 us, i.e. within the run-to-run
+// spread; the fixed ~14 us of this pass is launch ramp and tail, not the load depth).
+// Needs D % N == 0 and 16-byte aligned inputs.  grid = (ceil(D/(CW N)), T, 2).
+template <typename T, int CW, int RG, int U>
 __global__ void __launch_bounds__(256) lfd_stats_rows_kernel(const T* __restrict__ za, const T* __restrict__ zb, int B,
                                                              int Tn, int D, double* __restrict__ sums) {
   constexpr int N = Vec16<T>::N;
-  __shared__ double s_part[3][2][64][N];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  static_assert(CW * RG == 256, "256 threads");
+  __shared__ double s_part[RG - 1][2][CW][N];
+  const int tx = threadIdx.x % CW, ty = threadIdx.x / CW;
   const int t = blockIdx.y;
-  const int c = (blockIdx.x * 64 + tx) * N;
+  const int c = (blockIdx.x * CW + tx) * N;
   const T* z = (blockIdx.z == 0 ? za : zb) + static_cast<int64_t>(t) * D + c;
   const int64_t bstride = static_cast<int64_t>(Tn) * D;
   double s[N], q[N];
 #pragma unroll
   for (int e = 0; e < N; ++e) { s[e] = 0.0; q[e] = 0.0; }
   if (c < D) {
-    constexpr int U = 4;
     int b = ty;
-    for (; b + 4 * (U - 1) < B; b += 4 * U) {
+    for (; b + RG * (U - 1) < B; b += RG * U) {
       float x[U][N];
 #pragma unroll
-      for (int u = 0; u < U; ++u) Vec16<T>::unpack(ldg_stream_v4(z + (b + 4 * u) * bstride), x[u]);
+      for (int u = 0; u < U; ++u) Vec16<T>::unpack(ldg_stream_v4(z + (b + RG * u) * bstride), x[u]);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(256) lfd_stats_rows_kernel(const T* __restrict
         }
       }
     }
-    for (; b < B; b += 4) {
+    for (; b < B; b += RG) {
       float x[N];
       Vec16<T>::unpack(ldg_stream_v4(z + b * bstride), x);
 #pragma unroll
@@ -127,8 +131,11 @@ __global__ void __launch_bounds__(256) lfd_stats_rows_kernel(const T* __restrict
     double* out_s = sums + static_cast<int64_t>(blockIdx.z) * 2 * TD + static_cast<int64_t>(t) * D + c;
 #pragma unroll
     for (int e = 0; e < N; ++e) {
-      out_s[e] = ((s[e] + s_part[0][0][tx][e]) + s_part[1][0][tx][e]) + s_part[2][0][tx][e];
-      out_s[TD + e] = ((q[e] + s_part[0][1][tx][e]) + s_part[1][1][tx][e]) + s_part[2][1][tx][e];
+      double a = s[e], b2 = q[e];
+#pragma unroll
+      for (int g = 0; g < RG - 1; ++g) { a += s_part[g][0][tx][e]; b2 += s_part[g][1][tx][e]; }   // fixed order
+      out_s[e] = a;
+      out_s[TD + e] = b2;
     }
   }
 }
@@ -621,9 +628,17 @@ int launch_stats(const void* za, const void* zb, int dtype, int64_t B, int64_t T
   if (vec_ok(za, zb, dtype, D) && Tn < 65536) {
     KernelScope ks("lfd_stats_kernel", stream);
     constexpr int N = Vec16<T>::N;
-    dim3 grid(static_cast<unsigned>((D + 64 * N - 1) / (64 * N)), static_cast<unsigned>(Tn), 2);
-    lfd_stats_rows_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb),
-                                                       static_cast<int>(B), static_cast<int>(Tn), static_cast<int>(D), sums);
+    if (B <= 128) {
+      dim3 grid(static_cast<unsigned>((D + 32 * N - 1) / (32 * N)), static_cast<unsigned>(Tn), 2);
+      lfd_stats_rows_kernel<T, 32, 8, 8><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb),
+                                                                   static_cast<int>(B), static_cast<int>(Tn),
+                                                                   static_cast<int>(D), sums);
+    } else {
+      dim3 grid(static_cast<unsigned>((D + 64 * N - 1) / (64 * N)), static_cast<unsigned>(Tn), 2);
+      lfd_stats_rows_kernel<T, 64, 4, 4><<<grid, 256, 0, stream>>>(static_cast<const T*>(za), static_cast<const T*>(zb),
+                                                                   static_cast<int>(B), static_cast<int>(Tn),
+                                                                   static_cast<int>(D), sums);
+    }
     FDDM_LAUNCH_OK();
     return FDDM_OK;
   }

@@ -102,17 +102,29 @@ def symmetric_exchange_available(group=None, multicast: bool = False) -> bool:
     if torch.distributed.get_world_size(group) < 2:
         return False
     dev = torch.device("cuda", torch.cuda.current_device())
+
+    def all_ranks(ok: int) -> bool:
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
+        return bool(int(flag))
+
+    # two steps, so that a rank that cannot even allocate never leaves the others waiting in the rendezvous
     ok = 1
+    try:
+        import torch.distributed._symmetric_memory as symm
+        symm.empty(4, dtype=torch.float32, device=dev)
+    except Exception:                                            # noqa: BLE001 -- any failure means "not available"
+        ok = 0
+    if not all_ranks(ok):
+        return False
     try:
         ex = _SymmExchange.of(group)
         _, key = ex.buffer("probe", 4, torch.float32, dev)
         if multicast and not int(ex.bufs[key][1].multicast_ptr):
             ok = 0
-    except Exception:                                            # noqa: BLE001 -- any failure means "not available"
+    except Exception:                                            # noqa: BLE001
         ok = 0
-    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
-    return bool(int(flag))
+    return all_ranks(ok)
 
 
 def _comm_stream(dev: torch.device) -> torch.cuda.Stream:

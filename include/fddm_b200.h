@@ -255,7 +255,8 @@ int fddm_edit_distance(const int32_t* ref, const int64_t* ref_off, const int32_t
  *   max_ctas             upper bound on the CTAs of the kernel (0: the default, 32) -- the number of SMs to
  *                        reserve with fddm_set_sm_reserve when it runs under a persistent row kernel
  * Every rank must make the same call (same n, algo, max_ctas) in the same order; stream-ordered, CUDA-graph
- * capturable. */
+ * capturable.  Two calls that share signal pads must not execute concurrently (order them on one stream or with
+ * events, as the host mirror does); a rank that never makes the call leaves the others spinning in the barrier. */
 #define FDDM_XGPU_P2P 1
 #define FDDM_XGPU_NVLS 2
 int64_t fddm_xgpu_signal_pad_bytes(void);

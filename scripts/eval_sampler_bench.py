@@ -38,10 +38,11 @@ def main():
     cond[:, 0, 0] = torch.arange(B, device=dev)                 # the utterance index travels in cond
     sch = fb.DiscreteDiffusionScheduler(K=V, T=200, device=dev)
 
-    def dec(x, t, c):                                           # capturable: no host read
-        step = (t[:1] // 5 - 1).clamp(0, 3)
-        rows = c[:, 0, 0].long()
-        return torch.index_select(torch.index_select(logits, 0, step)[0], 0, rows)
+    flat = logits.view(4 * B, L, V)
+
+    def dec(x, t, c):                                           # capturable (no host read); cost ~ rows returned,
+        idx = (t // 5 - 1).clamp(0, 3) * B + c[:, 0, 0].long()  # so the B=1 calls are not charged for the whole batch
+        return torch.index_select(flat, 0, idx)
 
     mk = lambda: fb.DiffusionJumpySampler(sch, dec, K=V, T_train=200, T_infer=20, r=5, greedy=True,
                                           posterior_mode="map", sampling_mode=a.mode, device=dev)
